@@ -1,0 +1,600 @@
+// engine.cu — plan loader, run-time shape inference, arena planner and step executor.
+// Replaces the paddle.inference predictor runs behind reference backend/tools/ocr.py:27 and
+// backend/tools/subtitle_detect.py:25 (see include/vse_b200.h for the boundary).
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace vse {
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int pad8(int c) { return round_up(c, 8); }
+
+Engine::Engine(const vse_config& c) : cfg(c) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw CudaError{"no CUDA device available (this engine has no CPU fallback)"};
+    if (cfg.device < 0 || cfg.device >= ndev) throw InvalidArg{"device ordinal out of range"};
+    VSE_CUDA(cudaSetDevice(cfg.device));
+    VSE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+}
+
+size_t Engine::elt_size(const ValueRec& v) const {
+    if (v.dtype == DT_U8) return 1;
+    if (v.dtype == DT_F32) return 4;
+    return cfg.precision == VSE_PRECISION_FP32 ? 4 : 2;
+}
+
+int Engine::value_cs(const PlanData& pd, int vid) const {
+    const ValueRec& v = pd.values[vid];
+    const ValueRec& r = v.alias_of >= 0 ? pd.values[v.alias_of] : v;
+    if (r.kind == KIND_VEC) return r.channels;
+    if (r.dtype == DT_U8) return 4;            // BGRX
+    if (r.dtype == DT_F32) return r.channels;  // dense outputs
+    return pad8(r.channels);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan loading: re-lay every parameter for the kernels
+// ------------------------------------------------------------------------------------------------
+void Engine::load_plan(int which, const void* blob, size_t n) {
+    if (which < 0 || which > 1) throw InvalidArg{"plan index must be 0 (det) or 1 (rec)"};
+    LoadedPlan& lp = plans_[which];
+    lp.loaded = false;
+    std::string err = lp.data.parse(blob, n);
+    if (!err.empty()) throw InvalidArg{err};
+    prepare_plan(lp);
+    lp.loaded = true;
+}
+
+void Engine::prepare_plan(LoadedPlan& lp) {
+    const PlanData& pd = lp.data;
+    std::vector<float> host;
+    host.reserve(pd.weights.size() * 2 + 4096);
+    struct Off { size_t w = SIZE_MAX, bias = SIZE_MAX, ps = SIZE_MAX, pb = SIZE_MAX, g = SIZE_MAX, b = SIZE_MAX, sc = SIZE_MAX, sh = SIZE_MAX; };
+    std::vector<Off> offs(pd.steps.size());
+    lp.dev.assign(pd.steps.size(), StepDev{});
+    auto alloc = [&](size_t nfloats) {
+        size_t o = host.size();
+        host.resize(o + round_up(int(nfloats), 4), 0.f);
+        return o;
+    };
+    auto put_vec = [&](const float* src, int64_t n, int padded) -> size_t {
+        size_t o = alloc(padded);
+        if (src) std::memcpy(host.data() + o, src, sizeof(float) * size_t(std::min<int64_t>(n, padded)));
+        return o;
+    };
+    for (size_t k = 0; k < pd.steps.size(); k++) {
+        const StepRec& s = pd.steps[k];
+        StepDev& d = lp.dev[k];
+        Off& o = offs[k];
+        const int cin = s.p[P_CIN], cout = s.p[P_COUT];
+        switch (s.op) {
+            case OP_CONV:
+            case OP_STEM: {
+                const int kh = s.p[P_KH], kw = s.p[P_KW];
+                const int cin_pad = s.op == OP_STEM ? 4 : pad8(cin);
+                d.w_ci = round_up(cin_pad, 16);
+                d.w_co = round_up(cout, 64);
+                if (s.wsize[W_WEIGHT] != int64_t(cout) * kh * kw * cin) throw InvalidArg{"conv weight size mismatch"};
+                o.w = alloc(size_t(kh) * kw * d.w_ci * d.w_co);
+                const float* src = pd.w(s, W_WEIGHT);  // [cout][kh][kw][cin]
+                for (int co = 0; co < cout; co++)
+                    for (int t = 0; t < kh * kw; t++)
+                        for (int ci = 0; ci < cin; ci++)
+                            host[o.w + (size_t(t) * d.w_ci + ci) * d.w_co + co] = src[(size_t(co) * kh * kw + t) * cin + ci];
+                o.bias = put_vec(pd.w(s, W_BIAS), cout, d.w_co);
+                if (s.p[P_HAS_POST]) {
+                    o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, d.w_co);
+                    o.pb = put_vec(pd.w(s, W_POST_SHIFT), cout, d.w_co);
+                }
+                break;
+            }
+            case OP_DWCONV: {
+                const int kh = s.p[P_KH], kw = s.p[P_KW], cp = pad8(cin);
+                if (s.wsize[W_WEIGHT] != int64_t(kh) * kw * cin) throw InvalidArg{"dwconv weight size mismatch"};
+                o.w = alloc(size_t(kh) * kw * cp);
+                const float* src = pd.w(s, W_WEIGHT);  // [kh][kw][c]
+                for (int t = 0; t < kh * kw; t++)
+                    for (int c = 0; c < cin; c++) host[o.w + size_t(t) * cp + c] = src[size_t(t) * cin + c];
+                o.bias = put_vec(pd.w(s, W_BIAS), cout, cp);
+                if (s.p[P_HAS_POST]) {
+                    o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, cp);
+                    o.pb = put_vec(pd.w(s, W_POST_SHIFT), cout, cp);
+                }
+                break;
+            }
+            case OP_DECONV2: {
+                const int cip = pad8(cin), cop = pad8(cout);
+                if (s.wsize[W_WEIGHT] != int64_t(4) * cout * cin) throw InvalidArg{"deconv weight size mismatch"};
+                o.w = alloc(size_t(4) * cop * cip);
+                const float* src = pd.w(s, W_WEIGHT);  // [kh][kw][cout][cin]
+                for (int pos = 0; pos < 4; pos++)
+                    for (int co = 0; co < cout; co++)
+                        for (int ci = 0; ci < cin; ci++)
+                            host[o.w + (size_t(pos) * cop + co) * cip + ci] = src[(size_t(pos) * cout + co) * cin + ci];
+                o.bias = put_vec(pd.w(s, W_BIAS), cout, cop);
+                if (s.p[P_HAS_POST]) {
+                    o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, cop);
+                    o.pb = put_vec(pd.w(s, W_POST_SHIFT), cout, cop);
+                }
+                break;
+            }
+            case OP_VECLIN: {
+                if (s.wsize[W_WEIGHT] != int64_t(cout) * cin) throw InvalidArg{"veclin weight size mismatch"};
+                o.w = put_vec(pd.w(s, W_WEIGHT), int64_t(cout) * cin, cout * cin);
+                o.bias = put_vec(pd.w(s, W_BIAS), cout, cout);
+                if (s.p[P_HAS_POST]) {
+                    o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, cout);
+                    o.pb = put_vec(pd.w(s, W_POST_SHIFT), cout, cout);
+                }
+                break;
+            }
+            case OP_LAYERNORM: {
+                int c = pd.values[s.out].channels;
+                o.g = put_vec(pd.w(s, W_GAMMA), c, pad8(c));
+                o.b = put_vec(pd.w(s, W_BETA), c, pad8(c));
+                break;
+            }
+            case OP_ELTWISE: {
+                int c = pd.values[s.out].channels;
+                o.sc = put_vec(pd.w(s, W_SCALE), c, pad8(c));
+                o.sh = put_vec(pd.w(s, W_SHIFT), c, pad8(c));
+                break;
+            }
+            case OP_LSTM:
+                throw InvalidArg{"LSTM step (V2/ch_rec) is not supported by this build"};
+            default:
+                break;
+        }
+    }
+    lp.weights.reserve(host.size() * sizeof(float));
+    VSE_CUDA(cudaMemcpy(lp.weights.p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const float* base = lp.weights.as<float>();
+    auto ptr = [&](size_t off) -> const float* { return off == SIZE_MAX ? nullptr : base + off; };
+    for (size_t k = 0; k < pd.steps.size(); k++) {
+        StepDev& d = lp.dev[k];
+        const Off& o = offs[k];
+        d.w = ptr(o.w); d.bias = ptr(o.bias); d.post_scale = ptr(o.ps); d.post_shift = ptr(o.pb);
+        d.gamma = ptr(o.g); d.beta = ptr(o.b); d.scale = ptr(o.sc); d.shift = ptr(o.sh);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry inference + arena planning
+// ------------------------------------------------------------------------------------------------
+static Geo derive_geo(const Geo& in, int kh, int kw, int sh, int sw, int ph, int pw, bool ceil_mode) {
+    Geo g;
+    g.tab.resize(in.tab.size());
+    int64_t off = 0;
+    for (size_t i = 0; i < in.tab.size(); i++) {
+        const ImgTab& t = in.tab[i];
+        int ho, wo;
+        if (!ceil_mode) {
+            ho = (t.h + 2 * ph - kh) / sh + 1;
+            wo = (t.w + 2 * pw - kw) / sw + 1;
+        } else {
+            ho = (t.h + 2 * ph - kh + sh - 1) / sh + 1;
+            wo = (t.w + 2 * pw - kw + sw - 1) / sw + 1;
+            if ((ho - 1) * sh >= t.h + ph) ho--;
+            if ((wo - 1) * sw >= t.w + pw) wo--;
+        }
+        if (ho < 1 || wo < 1) throw InvalidArg{"image too small for this network"};
+        g.tab[i] = ImgTab{int(off), ho, wo, wo};
+        off += int64_t(ho) * wo;
+        g.max_pix = std::max(g.max_pix, ho * wo);
+    }
+    if (off > 0x7fffffffLL) throw InvalidArg{"batch too large (pixel index overflow)"};
+    g.total = off;
+    return g;
+}
+
+static Geo scale_geo(const Geo& in, int scale) {
+    Geo g;
+    g.tab.resize(in.tab.size());
+    int64_t off = 0;
+    for (size_t i = 0; i < in.tab.size(); i++) {
+        int ho = in.tab[i].h * scale, wo = in.tab[i].w * scale;
+        g.tab[i] = ImgTab{int(off), ho, wo, wo};
+        off += int64_t(ho) * wo;
+        g.max_pix = std::max(g.max_pix, ho * wo);
+    }
+    if (off > 0x7fffffffLL) throw InvalidArg{"batch too large (pixel index overflow)"};
+    g.total = off;
+    return g;
+}
+
+static bool same_geo(const Geo& a, const Geo& b) {
+    if (a.tab.size() != b.tab.size()) return false;
+    for (size_t i = 0; i < a.tab.size(); i++)
+        if (a.tab[i].h != b.tab[i].h || a.tab[i].w != b.tab[i].w) return false;
+    return true;
+}
+
+void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool keep_all) {
+    LoadedPlan& lp = plans_[which];
+    if (!lp.loaded) throw InvalidArg{which == 0 ? "detection plan not loaded" : "recognition plan not loaded"};
+    const PlanData& pd = lp.data;
+    ExecContext& cx = ctx_[which];
+    cx.geos.clear();
+    cx.vals.assign(pd.values.size(), ValueRt{});
+    cx.n_img = int(in_tab.size());
+    auto add_geo = [&](Geo&& g) -> int {
+        for (size_t i = 0; i < cx.geos.size(); i++)
+            if (same_geo(cx.geos[i], g)) return int(i);
+        cx.geos.push_back(std::move(g));
+        return int(cx.geos.size()) - 1;
+    };
+    {
+        Geo g;
+        g.tab = in_tab;
+        int64_t off = 0;
+        for (auto& t : g.tab) {
+            t.off = int(off);
+            off += int64_t(t.h) * t.w;
+            g.max_pix = std::max(g.max_pix, t.h * t.w);
+        }
+        g.total = off;
+        cx.geos.push_back(std::move(g));  // geo 0 keeps valid widths; never merged with others
+        cx.vals[pd.hdr.input_vid].geo = 0;
+    }
+    auto root_of = [&](int v) { return pd.values[v].alias_of >= 0 ? pd.values[v].alias_of : v; };
+    size_t scratch = 0;
+    for (size_t k = 0; k < pd.steps.size(); k++) {
+        const StepRec& s = pd.steps[k];
+        const int gin = s.ins[0] >= 0 ? cx.vals[s.ins[0]].geo : -1;
+        int gout = -1;
+        switch (s.op) {
+            case OP_CONV: case OP_STEM: case OP_DWCONV: {
+                if (gin < 0) throw InvalidArg{"conv input has no geometry"};
+                Geo g = derive_geo(cx.geos[gin], s.p[P_KH], s.p[P_KW], s.p[P_SH], s.p[P_SW], s.p[P_PH], s.p[P_PW], false);
+                gout = add_geo(std::move(g));
+                break;
+            }
+            case OP_POOL: {
+                Geo g = derive_geo(cx.geos[gin], s.p[P_KH], s.p[P_KW], s.p[P_SH], s.p[P_SW], s.p[P_PH], s.p[P_PW], s.p[P_CEIL] != 0);
+                gout = add_geo(std::move(g));
+                break;
+            }
+            case OP_DECONV2: gout = add_geo(scale_geo(cx.geos[gin], 2)); break;
+            case OP_UPSAMPLE: gout = add_geo(scale_geo(cx.geos[gin], s.p[P_SCALE])); break;
+            case OP_GPOOL: {
+                int cp = pad8(pd.values[s.ins[0]].channels);
+                scratch = std::max(scratch, size_t(cx.n_img) * 64 * cp * sizeof(float));
+                gout = -1;
+                break;
+            }
+            case OP_VECLIN: gout = -1; break;
+            default: {
+                // same geometry as input; geo 0 (input with valid widths) is never propagated
+                if (gin == 0) {
+                    Geo g = cx.geos[0];
+                    for (auto& t : g.tab) t.vw = t.w;
+                    gout = add_geo(std::move(g));
+                } else gout = gin;
+                break;
+            }
+        }
+        // outputs that alias into a concat root share the root's geometry
+        cx.vals[s.out].geo = gout;
+        int r = root_of(s.out);
+        if (r != s.out) {
+            if (cx.vals[r].geo >= 0 && gout >= 0 && !same_geo(cx.geos[cx.vals[r].geo], cx.geos[gout]))
+                throw InvalidArg{"concat inputs with different geometry"};
+            cx.vals[r].geo = gout;
+        }
+        if (s.op == OP_COPY) cx.vals[s.out].geo = gin;
+    }
+    // views of a root that were assigned before the root got its geometry
+    for (size_t v = 0; v < pd.values.size(); v++) {
+        int r = root_of(int(v));
+        if (r != int(v) && cx.vals[v].geo < 0) cx.vals[v].geo = cx.vals[r].geo;
+        if (r != int(v) && cx.vals[r].geo < 0) cx.vals[r].geo = cx.vals[v].geo;
+    }
+    // H==1 requirement of [B,T,C] views
+    for (int i = 0; i < 8; i++) {
+        int v = pd.hdr.h1_values[i];
+        if (v < 0) continue;
+        int g = cx.vals[v].geo;
+        if (g >= 0)
+            for (auto& t : cx.geos[g].tab)
+                if (t.h != 1) throw InvalidArg{"recognition input height does not reduce to 1 (wrong rec_image_h?)"};
+    }
+    // device tables
+    size_t ntab = 0;
+    for (auto& g : cx.geos) { g.tab_off = ntab; ntab += g.tab.size(); }
+    pin_.reserve(ntab * sizeof(ImgTab));
+    for (auto& g : cx.geos) std::memcpy(pin_.as<ImgTab>() + g.tab_off, g.tab.data(), g.tab.size() * sizeof(ImgTab));
+    cx.tabs.reserve(ntab * sizeof(ImgTab));
+    VSE_CUDA(cudaMemcpyAsync(cx.tabs.p, pin_.p, ntab * sizeof(ImgTab), cudaMemcpyHostToDevice, stream));
+    VSE_CUDA(cudaStreamSynchronize(stream));  // pin_ is reused by the caller
+
+    // arena planning (first-fit free list over root buffers)
+    struct Block { size_t off, size; };
+    std::vector<Block> free_list;
+    size_t top = 0;
+    auto arena_alloc = [&](size_t n) -> size_t {
+        n = (n + 255) & ~size_t(255);
+        for (size_t i = 0; i < free_list.size(); i++) {
+            if (free_list[i].size >= n) {
+                size_t o = free_list[i].off;
+                free_list[i].off += n;
+                free_list[i].size -= n;
+                if (free_list[i].size == 0) free_list.erase(free_list.begin() + i);
+                return o;
+            }
+        }
+        size_t o = top;
+        top += n;
+        return o;
+    };
+    auto arena_free = [&](size_t off, size_t n) {
+        n = (n + 255) & ~size_t(255);
+        free_list.push_back(Block{off, n});
+        std::sort(free_list.begin(), free_list.end(), [](const Block& a, const Block& b) { return a.off < b.off; });
+        for (size_t i = 0; i + 1 < free_list.size();) {
+            if (free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+                free_list[i].size += free_list[i + 1].size;
+                free_list.erase(free_list.begin() + i + 1);
+            } else i++;
+        }
+        if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
+            top = free_list.back().off;
+            free_list.pop_back();
+        }
+    };
+    size_t peak = 0;
+    auto root_bytes = [&](int v) -> size_t {
+        const ValueRec& r = pd.values[v];
+        if (r.kind == KIND_VEC) return size_t(cx.n_img) * r.channels * sizeof(float);
+        int g = cx.vals[v].geo;
+        if (g < 0) throw InvalidArg{"value without geometry: " + std::to_string(v)};
+        return size_t(cx.geos[g].total) * value_cs(pd, v) * elt_size(r);
+    };
+    const int nsteps = int(pd.steps.size());
+    for (int k = -1; k <= nsteps; k++) {
+        for (size_t v = 0; v < pd.values.size(); v++) {
+            const ValueRec& r = pd.values[v];
+            if (r.alias_of >= 0 || r.first_def != k || r.first_def == -2) continue;
+            if (int(v) == pd.hdr.input_vid) continue;  // the input lives in caller memory
+            ValueRt& rt = cx.vals[v];
+            rt.bytes = root_bytes(int(v));
+            rt.off = arena_alloc(rt.bytes);
+            rt.live = true;
+            peak = std::max(peak, top);
+        }
+        if (!keep_all && k >= 0)
+            for (size_t v = 0; v < pd.values.size(); v++) {
+                const ValueRec& r = pd.values[v];
+                if (r.alias_of >= 0 || r.first_def == -2 || r.last_use != k || !cx.vals[v].live) continue;
+                if (int(v) == pd.hdr.input_vid) continue;
+                arena_free(cx.vals[v].off, cx.vals[v].bytes);
+            }
+    }
+    cx.scratch_off = (peak + 255) & ~size_t(255);
+    cx.scratch_bytes = scratch;
+    cx.arena_bytes = cx.scratch_off + scratch + 256;
+    arena_[which].reserve(cx.arena_bytes);
+}
+
+void* Engine::vptr(int which, int vid) const {
+    const PlanData& pd = plans_[which].data;
+    const ValueRec& v = pd.values[vid];
+    int r = v.alias_of >= 0 ? v.alias_of : vid;
+    const ValueRt& rt = ctx_[which].vals[r];
+    char* base = static_cast<char*>(arena_[which].p) + rt.off;
+    if (v.alias_of >= 0) base += size_t(v.alias_coff) * elt_size(pd.values[r]);
+    return base;
+}
+
+const void* Engine::value_ptr(int which, int vid, int* cs, const Geo** geo) {
+    const PlanData& pd = plans_[which].data;
+    if (cs) *cs = value_cs(pd, vid);
+    if (geo) {
+        int g = ctx_[which].vals[vid].geo;
+        *geo = g >= 0 ? &ctx_[which].geos[g] : nullptr;
+    }
+    return vptr(which, vid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// execution
+// ------------------------------------------------------------------------------------------------
+void Engine::run_plan(int which, const std::vector<ImgTab>& in_tab, const uint8_t* input_dev, bool keep_all) {
+    build_context(which, in_tab, keep_all);
+    // the input value is external memory: stash its pointer via a fake arena offset trick
+    input_ptr_[which] = input_dev;
+    exec_steps(which);
+}
+
+void Engine::exec_steps(int which) {
+    LoadedPlan& lp = plans_[which];
+    const PlanData& pd = lp.data;
+    ExecContext& cx = ctx_[which];
+    const int prec = cfg.precision == VSE_PRECISION_FP32 ? 1 : 0;
+    const ImgTab* dtab = cx.tabs.as<ImgTab>();
+    auto tab_of = [&](int vid) -> const ImgTab* {
+        int g = cx.vals[vid].geo;
+        return g >= 0 ? dtab + cx.geos[g].tab_off : nullptr;
+    };
+    auto geo_of = [&](int vid) -> const Geo& { return cx.geos[cx.vals[vid].geo]; };
+    auto ptr_of = [&](int vid) -> void* {
+        if (vid == pd.hdr.input_vid) return const_cast<uint8_t*>(input_ptr_[which]);
+        return vptr(which, vid);
+    };
+    auto fill_epi = [&](const StepRec& s, const StepDev& d, Epilogue& e) {
+        e.bias = d.bias;
+        e.post_scale = s.p[P_HAS_POST] ? d.post_scale : nullptr;
+        e.post_shift = s.p[P_HAS_POST] ? d.post_shift : nullptr;
+        e.act = s.p[P_ACT];
+        e.act2 = s.p[P_ACT2];
+        e.hs_slope = s.f[F_HS_SLOPE];
+        e.hs_offset = s.f[F_HS_OFFSET];
+        if (s.p[P_HAS_RES]) {
+            e.res = ptr_of(s.ins[1]);
+            e.res_cs = value_cs(pd, s.ins[1]);
+        }
+    };
+    for (size_t k = 0; k < pd.steps.size(); k++) {
+        const StepRec& s = pd.steps[k];
+        const StepDev& d = lp.dev[k];
+        const ValueRec& vo = pd.values[s.out];
+        const int out_f32 = vo.dtype == DT_F32 && vo.kind == KIND_IMG;
+        switch (s.op) {
+            case OP_CONV: case OP_STEM: case OP_DWCONV: case OP_DECONV2: {
+                ConvArgs a;
+                a.in = ptr_of(s.ins[0]);
+                a.out = ptr_of(s.out);
+                a.w = d.w;
+                fill_epi(s, d, a.epi);
+                a.tin = tab_of(s.ins[0]);
+                a.tout = tab_of(s.out);
+                a.n_img = cx.n_img;
+                a.max_out_pix = geo_of(s.out).max_pix;
+                a.in_u8 = s.op == OP_STEM;
+                a.cin_pad = a.in_u8 ? 4 : pad8(s.p[P_CIN]);
+                a.in_cs = value_cs(pd, s.ins[0]);
+                a.cout_store = pad8(s.p[P_COUT]);
+                a.out_cs = value_cs(pd, s.out);
+                a.w_ci = d.w_ci;
+                a.w_co = d.w_co;
+                a.kh = s.p[P_KH]; a.kw = s.p[P_KW]; a.sh = s.p[P_SH]; a.sw = s.p[P_SW]; a.ph = s.p[P_PH]; a.pw = s.p[P_PW];
+                a.out_f32 = out_f32;
+                for (int i = 0; i < 3; i++) { a.nscale[i] = pd.hdr.norm_scale[i]; a.nshift[i] = pd.hdr.norm_shift[i]; }
+                if (s.op == OP_DWCONV) {
+                    if (out_f32) throw InvalidArg{"depthwise conv cannot produce a fetched output"};
+                    launch_dwconv(a, prec, stream);
+                } else if (s.op == OP_DECONV2) {
+                    launch_deconv2(a, s.p[P_COUT], prec, stream);
+                } else {
+                    if (out_f32) a.cout_store = s.p[P_COUT];
+                    launch_conv(which, int(k), a, prec);
+                }
+                launches++;
+                break;
+            }
+            case OP_GPOOL: {
+                const int cp = pad8(pd.values[s.ins[0]].channels);
+                const Geo& g = geo_of(s.ins[0]);
+                int splits = std::min(64, std::max(1, g.max_pix / 2048));
+                float* partial = reinterpret_cast<float*>(static_cast<char*>(arena_[which].p) + cx.scratch_off);
+                launch_gpool(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), cp, tab_of(s.ins[0]), cx.n_img, g.max_pix, partial,
+                             splits, static_cast<float*>(ptr_of(s.out)), vo.channels, prec, stream);
+                launches += 2;
+                break;
+            }
+            case OP_VECLIN: {
+                Epilogue e;
+                fill_epi(s, d, e);
+                launch_veclin(static_cast<const float*>(ptr_of(s.ins[0])), s.p[P_CIN], static_cast<float*>(ptr_of(s.out)),
+                              s.p[P_COUT], d.w, e, cx.n_img, stream);
+                launches++;
+                break;
+            }
+            case OP_CHSCALE: {
+                const Geo& g = geo_of(s.out);
+                launch_chscale(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), ptr_of(s.out), value_cs(pd, s.out), pad8(vo.channels),
+                               static_cast<const float*>(ptr_of(s.ins[1])), pd.values[s.ins[1]].channels, s.p[P_RESIDUAL],
+                               tab_of(s.out), cx.n_img, g.max_pix, prec, stream);
+                launches++;
+                break;
+            }
+            case OP_POOL: {
+                launch_pool(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), ptr_of(s.out), value_cs(pd, s.out), pad8(vo.channels),
+                            tab_of(s.ins[0]), tab_of(s.out), cx.n_img, geo_of(s.out).max_pix, s.p[P_KH], s.p[P_KW], s.p[P_SH],
+                            s.p[P_SW], s.p[P_PH], s.p[P_PW], s.p[P_IS_MAX], s.p[P_EXCLUSIVE], prec, stream);
+                launches++;
+                break;
+            }
+            case OP_UPSAMPLE: {
+                const void* add = s.p[P_HAS_ADD] ? ptr_of(s.ins[1]) : nullptr;
+                int add_cs = s.p[P_HAS_ADD] ? value_cs(pd, s.ins[1]) : 0;
+                launch_upsample(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), add, add_cs, ptr_of(s.out), value_cs(pd, s.out),
+                                pad8(vo.channels), tab_of(s.ins[0]), tab_of(s.out), cx.n_img, geo_of(s.out).max_pix,
+                                s.p[P_SCALE], prec, stream);
+                launches++;
+                break;
+            }
+            case OP_ADD: {
+                launch_add(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), ptr_of(s.ins[1]), value_cs(pd, s.ins[1]), ptr_of(s.out),
+                           value_cs(pd, s.out), pad8(vo.channels), vo.channels, geo_of(s.out).total, s.p[P_ACT], out_f32, prec,
+                           stream);
+                launches++;
+                break;
+            }
+            case OP_ELTWISE: {
+                if (vo.kind == KIND_VEC) throw InvalidArg{"standalone elementwise op on a pooled vector"};
+                launch_eltwise(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), ptr_of(s.out), value_cs(pd, s.out), pad8(vo.channels),
+                               vo.channels, geo_of(s.out).total, d.scale, d.shift, s.p[P_ACT], s.f[F_HS_SLOPE], s.f[F_HS_OFFSET],
+                               out_f32, prec, stream);
+                launches++;
+                break;
+            }
+            case OP_COPY: {
+                // copy ins[0] into channels [coff, coff+c) of the concat root `out`
+                const int coff = s.p[P_SCALE], c = s.p[P_COUT];
+                char* dst = static_cast<char*>(ptr_of(s.out)) + size_t(coff) * elt_size(vo);
+                launch_copy(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), dst, value_cs(pd, s.out), pad8(c), geo_of(s.ins[0]).total, prec,
+                            stream);
+                launches++;
+                break;
+            }
+            case OP_LAYERNORM: {
+                launch_layernorm(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), ptr_of(s.out), value_cs(pd, s.out), vo.channels,
+                                 geo_of(s.out).total, d.gamma, d.beta, s.f[F_EPS], prec, stream);
+                launches++;
+                break;
+            }
+            case OP_ATTN: {
+                const Geo& g = geo_of(s.out);
+                if (s.p[P_DIM] > 32) throw InvalidArg{"attention head dim > 32"};
+                if (attention_smem_bytes(g.max_pix, s.p[P_DIM]) > 200 * 1024) throw InvalidArg{"text line too long for attention kernel"};
+                launch_attention(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), ptr_of(s.out), value_cs(pd, s.out), s.p[P_HEADS],
+                                 s.p[P_DIM], s.f[F_QSCALE], tab_of(s.out), cx.n_img, g.max_pix, prec, stream);
+                launches++;
+                break;
+            }
+            case OP_SOFTMAX: {
+                launch_softmax(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), static_cast<float*>(ptr_of(s.out)), vo.channels,
+                               geo_of(s.out).total, prec, stream);
+                launches++;
+                break;
+            }
+            default:
+                throw InvalidArg{std::string("unsupported step ") + kOpNames[s.op]};
+        }
+    }
+    VSE_CUDA(cudaGetLastError());
+}
+
+void Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
+    (void)which;
+    (void)step;
+    launch_conv_simt(a, prec, stream);
+}
+
+int64_t Engine::get_value(int which, int vid, float* out, int64_t cap, int32_t* channels) {
+    const PlanData& pd = plans_[which].data;
+    if (vid < 0 || vid >= int(pd.values.size())) throw InvalidArg{"value id out of range"};
+    const ValueRec& v = pd.values[vid];
+    const ExecContext& cx = ctx_[which];
+    int r = v.alias_of >= 0 ? v.alias_of : vid;
+    if (vid != pd.hdr.input_vid && !cx.vals[r].live) return 0;  // fused away
+    if (channels) *channels = v.channels;
+    int64_t pixels = v.kind == KIND_VEC ? cx.n_img : cx.geos[cx.vals[vid].geo].total;
+    int64_t n = pixels * v.channels;
+    if (!out) return n;
+    if (cap < n) throw InvalidArg{"output buffer too small"};
+    if (v.dtype == DT_U8) throw InvalidArg{"cannot dump the uint8 input"};
+    dbg_.reserve(size_t(n) * sizeof(float));
+    const int prec = cfg.precision == VSE_PRECISION_FP32 ? 1 : 0;
+    bool is_f32 = v.dtype == DT_F32 || v.kind == KIND_VEC;
+    launch_to_float(vptr(which, vid), value_cs(pd, vid), is_f32, dbg_.as<float>(), v.channels, pixels, prec, stream);
+    VSE_CUDA(cudaMemcpyAsync(out, dbg_.p, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    VSE_CUDA(cudaStreamSynchronize(stream));
+    return n;
+}
+
+}  // namespace vse

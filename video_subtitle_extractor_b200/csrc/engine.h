@@ -1,0 +1,167 @@
+// engine.h — internal C++ interface of the B200 engine (plan executor + frame pipeline).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/vse_b200.h"
+#include "nn_kernels.h"
+#include "plan.h"
+
+namespace vse {
+
+struct CudaError {
+    std::string msg;
+};
+#define VSE_CUDA(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            throw ::vse::CudaError{std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                   std::to_string(__LINE__) + ")"};                                       \
+    } while (0)
+
+struct InvalidArg {
+    std::string msg;
+};
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + (n >> 3) + 256;
+        VSE_CUDA(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        VSE_CUDA(cudaMallocHost(&p, n + (n >> 3) + 256));
+        cap = n + (n >> 3) + 256;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// device-side parameters of one step, in kernel-ready layout
+struct StepDev {
+    const float* w = nullptr;
+    const float* bias = nullptr;
+    const float* post_scale = nullptr;
+    const float* post_shift = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+    const void* w_tc = nullptr;  // half, K-major [cout_pad][k_pad] for the tensor-core path
+    int w_ci = 0, w_co = 0, k_pad = 0, n_pad = 0;
+};
+
+struct Geo {
+    std::vector<ImgTab> tab;
+    int64_t total = 0;
+    int max_pix = 0;
+    size_t tab_off = 0;  // offset (in ImgTab units) inside the context's device table
+};
+
+struct ValueRt {
+    int geo = -1;       // index into ExecContext::geos (images) ; -1 for vectors
+    size_t off = 0;     // byte offset of the ROOT buffer in the arena
+    size_t bytes = 0;   // size of the root buffer
+    bool live = false;
+};
+
+struct LoadedPlan {
+    PlanData data;
+    std::vector<StepDev> dev;
+    DevBuf weights;  // all device parameters
+    bool loaded = false;
+};
+
+// one execution of a plan on a concrete batch geometry
+struct ExecContext {
+    std::vector<Geo> geos;
+    std::vector<ValueRt> vals;
+    DevBuf tabs;      // all ImgTab tables
+    size_t arena_bytes = 0;
+    size_t scratch_off = 0, scratch_bytes = 0;
+    int n_img = 0;
+};
+
+class Engine {
+  public:
+    explicit Engine(const vse_config& cfg);
+    ~Engine();
+    void load_plan(int which, const void* blob, size_t n);
+
+    // Builds geometry + memory plan for `which` on images (h, w[i], valid_w[i]) and runs it.
+    // Input pixels (uint8 BGRX) must already be in `input_dev` laid out image after image.
+    void run_plan(int which, const std::vector<ImgTab>& in_tab, const uint8_t* input_dev, bool keep_all);
+    int64_t get_value(int which, int vid, float* out, int64_t cap, int32_t* channels);
+    const void* value_ptr(int which, int vid, int* cs, const Geo** geo);
+
+    void run_frames(const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* stride, int n,
+                    int mem_kind, vse_result* out, bool det_only);
+
+    // debug hooks
+    void debug_run_plan(int which, const uint8_t* const* images, int n, int h, const int32_t* w, const int32_t* valid_w,
+                        bool keep_all);
+    void debug_resize(const uint8_t* src, int sh, int sw, int stride, uint8_t* dst, int dh, int dw);
+    void debug_db_post(const float* prob, int rh, int rw, int src_h, int src_w, float* quads, float* scores, int cap,
+                       int* n_out);
+    void debug_crop(const uint8_t* frame, int h, int w, const float* quad, uint8_t* out, int cap, int* oh, int* ow);
+
+    std::string last_error;
+    int64_t launches = 0;
+    vse_config cfg;
+    cudaStream_t stream = nullptr;
+
+  private:
+    void prepare_plan(LoadedPlan& lp);
+    void build_context(int which, const std::vector<ImgTab>& in_tab, bool keep_all);
+    void exec_steps(int which);
+    size_t elt_size(const ValueRec& v) const;
+    int value_cs(const PlanData& pd, int vid) const;  // channel stride in elements
+    void* vptr(int which, int vid) const;
+    void launch_conv(int which, int step, const ConvArgs& a, int prec);
+    const uint8_t* input_ptr_[2] = {nullptr, nullptr};
+
+    LoadedPlan plans_[2];
+    ExecContext ctx_[2];
+    DevBuf arena_[2];
+    DevBuf dbg_;
+    PinnedBuf pin_;
+
+    // pipeline state (pipeline.cu)
+    struct Pipeline;
+    Pipeline* pipe_ = nullptr;
+    friend struct Pipeline;
+};
+
+}  // namespace vse

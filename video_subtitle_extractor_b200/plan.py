@@ -812,7 +812,7 @@ class Plan:
         vrec = b""
         for v in self.values:
             root = v.alias_of if v.alias_of >= 0 else v.vid
-            a, b = live.get(root, (0, 0))
+            a, b = live.get(root, (-2, -2))   # -2: value eliminated by fusion, never materialised
             vrec += struct.pack("<8i", v.channels, v.cstride, v.kind, v.dtype, v.alias_of, v.alias_coff, a, b)
         srec = b""
         for s in self.steps:
@@ -873,6 +873,24 @@ def compile_model(model: Model, name: str = "", norm_scale=(1.0, 1.0, 1.0), norm
     nodes = [n for n, k in zip(nodes, keep_nodes) if k]
     nodes = _fuse(low.values, nodes, keep=set(out_vids))
     nodes = _resolve_concat(low.values, nodes, low.input_vid)
+    # fetched values leave the engine as dense float32 [pixels][channels]
+    cons = _consumers(nodes)
+    producer = {s.out: s for s in nodes if s.op != OP_COPY}
+    for k, v in enumerate(list(out_vids)):
+        val = low.values[v]
+        if val.dtype == DT_F32:
+            continue
+        direct = (v in producer and producer[v].op in (OP_CONV, OP_DECONV2, OP_ELTWISE, OP_ADD) and not cons.get(v)
+                  and val.alias_of < 0 and not any(x.alias_of == v for x in low.values))
+        if direct:
+            val.dtype = DT_F32
+        else:
+            c = val.channels
+            nv = Value(len(low.values), c, KIND_IMG, DT_F32)
+            low.values.append(nv)
+            nodes.append(Step(OP_ELTWISE, [v], nv.vid, dict(act=ACT_NONE),
+                              dict(scale=np.ones(c, np.float32), shift=np.zeros(c, np.float32))))
+            out_vids[k] = nv.vid
     return Plan(values=low.values, steps=nodes, input_vid=low.input_vid, output_vids=out_vids, name=name,
                 norm_scale=tuple(norm_scale), norm_shift=tuple(norm_shift),
                 h1_values=tuple(sorted(getattr(low, "h1_values", set()))))
@@ -882,3 +900,72 @@ def compile_model(model: Model, name: str = "", norm_scale=(1.0, 1.0, 1.0), norm
 DET_NORM = (tuple(1.0 / (255.0 * s) for s in (0.229, 0.224, 0.225)),
             tuple(-m / s for m, s in zip((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))))
 REC_NORM = ((1.0 / 127.5,) * 3, (-1.0,) * 3)
+
+
+def deserialize(blob: bytes) -> Plan:
+    """Inverse of ``Plan.serialize`` (tests rebuild the step list from a shipped .vsep file)."""
+    hdr_fmt = "<6Iqi4i8i6f64s"
+    hsz = struct.calcsize(hdr_fmt)
+    f = struct.unpack_from(hdr_fmt, blob, 0)
+    magic, version, n_values, n_steps = f[0], f[1], f[2], f[3]
+    if magic != PLAN_MAGIC or version != PLAN_VERSION:
+        raise PlanError("bad plan blob")
+    n_weights, input_vid = f[6], f[7]
+    outs = [v for v in f[8:12] if v >= 0]
+    h1 = [v for v in f[12:20] if v >= 0]
+    norm = f[20:26]
+    name = f[26].split(b"\0")[0].decode()
+    pos = hsz
+    values: List[Value] = []
+    for vid in range(n_values):
+        ch, cs, kind, dtype, alias_of, alias_coff, a, b = struct.unpack_from("<8i", blob, pos)
+        pos += 32
+        values.append(Value(vid, ch, kind, dtype, alias_of, alias_coff))
+    step_fmt = f"<i{_N_INS}ii{_N_P}i{_N_F}f{_N_W}q{_N_W}q"
+    ssz = struct.calcsize(step_fmt)
+    wbase = pos + ssz * n_steps
+    weights = np.frombuffer(blob, dtype=np.float32, count=n_weights, offset=wbase)
+    steps: List[Step] = []
+    for _ in range(n_steps):
+        r = struct.unpack_from(step_fmt, blob, pos)
+        pos += ssz
+        op = r[0]
+        ins = [v for v in r[1:1 + _N_INS] if v >= 0]
+        out = r[1 + _N_INS]
+        pv = r[2 + _N_INS:2 + _N_INS + _N_P]
+        fv = r[2 + _N_INS + _N_P:2 + _N_INS + _N_P + _N_F]
+        wo = r[2 + _N_INS + _N_P + _N_F:2 + _N_INS + _N_P + _N_F + _N_W]
+        wn = r[2 + _N_INS + _N_P + _N_F + _N_W:]
+        p: Dict[str, Any] = {k: pv[i] for i, k in enumerate(_P_SLOTS)}
+        p.update({k: fv[i] for i, k in enumerate(_F_SLOTS)})
+        if op == OP_COPY:
+            p["coff"], p["c"] = p["scale"], p["cout"]
+        if op == OP_LSTM:
+            p["hidden"], p["layers"], p["ndir"] = p["heads"], p["dim"], p["scale"]
+        w: Dict[str, np.ndarray] = {}
+        for j, k in enumerate(_W_SLOTS):
+            if wo[j] >= 0:
+                w[k] = weights[wo[j]:wo[j] + wn[j]]
+        cin, cout, kh, kw = p["cin"], p["cout"], p["kh"], p["kw"]
+        if op in (OP_CONV, OP_STEM):
+            w["weight"] = w["weight"].reshape(cout, kh, kw, cin)
+        elif op == OP_DWCONV:
+            w["weight"] = w["weight"].reshape(kh, kw, cin)
+        elif op == OP_DECONV2:
+            w["weight"] = w["weight"].reshape(2, 2, cout, cin)
+        elif op == OP_VECLIN:
+            w["weight"] = w["weight"].reshape(cout, cin)
+        elif op == OP_LSTM:
+            flat = w.pop("weight")
+            hidden, layers, ndir, c_in = p["hidden"], p["layers"], p["ndir"], cin
+            o = 0
+            for l in range(layers):
+                isz = c_in if l == 0 else hidden * ndir
+                for d in range(ndir):
+                    k = l * ndir + d
+                    w[f"w_ih{k}"] = flat[o:o + 4 * hidden * isz].reshape(4 * hidden, isz); o += 4 * hidden * isz
+                    w[f"w_hh{k}"] = flat[o:o + 4 * hidden * hidden].reshape(4 * hidden, hidden); o += 4 * hidden * hidden
+                    w[f"b{k}"] = flat[o:o + 4 * hidden]; o += 4 * hidden
+        steps.append(Step(op, ins, out, p, w))
+    return Plan(values=values, steps=steps, input_vid=input_vid, output_vids=outs, name=name,
+                norm_scale=tuple(norm[:3]), norm_shift=tuple(norm[3:]), h1_values=tuple(h1))
