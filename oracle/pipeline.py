@@ -33,7 +33,40 @@ class OracleResult:
     det_scores: List[float] = field(default_factory=list)
 
 
+class _PlanNet:
+    """Adapter: run a packed plan (the committed .vsep files) on the CPU plan interpreter with the
+    GraphInterpreter calling convention (float NCHW in, reference-layout outputs out).  Used where the reference
+    tree is absent (GPU box); tests/test_plan_cpu.py proves plan == graph where it is present."""
+
+    def __init__(self, blob: bytes, is_rec: bool):
+        from video_subtitle_extractor_b200 import plan as P
+        from .plan_interp import PlanInterpreter
+        self.interp = PlanInterpreter(P.deserialize(blob))
+        self.is_rec = is_rec
+
+    def run(self, x):
+        import torch
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        outs = self.interp.run(x.float())
+        if self.is_rec:  # [B, C, 1, T] -> [B, T, C]
+            outs = [o[:, :, 0, :].permute(0, 2, 1).contiguous() for o in outs]
+        return outs
+
+
 class OraclePipeline:
+    @classmethod
+    def from_plans(cls, det_blob: bytes, rec_blob: Optional[bytes] = None, **kw) -> "OraclePipeline":
+        self = cls.__new__(cls)
+        self.det = _PlanNet(det_blob, False)
+        self.rec = _PlanNet(rec_blob, True) if rec_blob else None
+        self.rec_batch_num = kw.get("rec_batch_num", 6)
+        shape = kw.get("rec_image_shape", (3, 48, 320))
+        self.rec_h, self.rec_w = shape[1], shape[2]
+        self.det_fetch = 0
+        self.limit_side_len = kw.get("limit_side_len", 960)
+        return self
+
     def __init__(self, det_model_dir: str, rec_model_dir: Optional[str] = None, rec_batch_num: int = 6,
                  rec_image_shape: Tuple[int, int, int] = (3, 48, 320), det_fetch: int = 0,
                  limit_side_len: int = 960):

@@ -22,6 +22,12 @@ static int guarded(vse_engine* e, F&& f) {
     } catch (const vse::InvalidArg& ia) {
         if (e) e->impl->last_error = ia.msg; else g_create_error = ia.msg;
         return VSE_ERR_INVALID;
+    } catch (const vse::CapacityError& ce) {
+        if (e) e->impl->last_error = ce.msg; else g_create_error = ce.msg;
+        return VSE_ERR_CAPACITY;
+    } catch (const vse::StateError& se) {
+        if (e) e->impl->last_error = se.msg; else g_create_error = se.msg;
+        return VSE_ERR_STATE;
     } catch (const std::bad_alloc&) {
         if (e) e->impl->last_error = "host allocation failed"; else g_create_error = "host allocation failed";
         return VSE_ERR_INVALID;
@@ -46,7 +52,7 @@ void vse_default_config(vse_config* cfg) {
     cfg->rec_image_h = 48;
     cfg->rec_image_w = 320;
     cfg->rec_batch_num = 6;
-    cfg->max_boxes_per_frame = 64;
+    cfg->max_boxes_per_frame = 128;
     cfg->flags = 0;
 }
 

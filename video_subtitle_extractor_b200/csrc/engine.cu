@@ -43,6 +43,7 @@ void Engine::load_plan(int which, const void* blob, size_t n) {
     if (which < 0 || which > 1) throw InvalidArg{"plan index must be 0 (det) or 1 (rec)"};
     LoadedPlan& lp = plans_[which];
     lp.loaded = false;
+    last_tab_[which].clear();
     std::string err = lp.data.parse(blob, n);
     if (!err.empty()) throw InvalidArg{err};
     prepare_plan(lp);
@@ -403,7 +404,17 @@ const void* Engine::value_ptr(int which, int vid, int* cs, const Geo** geo) {
 // execution
 // ------------------------------------------------------------------------------------------------
 void Engine::run_plan(int which, const std::vector<ImgTab>& in_tab, const uint8_t* input_dev, bool keep_all) {
-    build_context(which, in_tab, keep_all);
+    // geometry + arena plan are reused when the batch has the same shapes as the previous call (the usual case for
+    // the detector: every frame of a video resizes to the same map)
+    bool same = plans_[which].loaded && last_keep_all_[which] == keep_all && last_tab_[which].size() == in_tab.size();
+    for (size_t i = 0; same && i < in_tab.size(); i++)
+        same = last_tab_[which][i].h == in_tab[i].h && last_tab_[which][i].w == in_tab[i].w && last_tab_[which][i].vw == in_tab[i].vw;
+    if (!same) {
+        last_tab_[which].clear();
+        build_context(which, in_tab, keep_all);
+        last_tab_[which] = in_tab;
+        last_keep_all_[which] = keep_all;
+    }
     // the input value is external memory: stash its pointer via a fake arena offset trick
     input_ptr_[which] = input_dev;
     exec_steps(which);

@@ -11,6 +11,7 @@
 #include "../../include/vse_b200.h"
 #include "nn_kernels.h"
 #include "plan.h"
+#include "postproc.cuh"
 
 namespace vse {
 
@@ -26,6 +27,12 @@ struct CudaError {
     } while (0)
 
 struct InvalidArg {
+    std::string msg;
+};
+struct CapacityError {
+    std::string msg;
+};
+struct StateError {
     std::string msg;
 };
 
@@ -137,6 +144,12 @@ class Engine {
                        int* n_out);
     void debug_crop(const uint8_t* frame, int h, int w, const float* quad, uint8_t* out, int cap, int* oh, int* ow);
 
+    // pipeline state (pipeline.cu)
+    struct Pipeline;
+    void ensure_pipeline();
+    // DB post-process of a device-resident probability map; results land in the pipeline's pinned h_out buffer
+    void db_post_device(const float* prob, const std::vector<DetFrame>& frames, bool reading_order);
+
     std::string last_error;
     int64_t launches = 0;
     vse_config cfg;
@@ -158,10 +171,9 @@ class Engine {
     DevBuf dbg_;
     PinnedBuf pin_;
 
-    // pipeline state (pipeline.cu)
-    struct Pipeline;
     Pipeline* pipe_ = nullptr;
-    friend struct Pipeline;
+    std::vector<ImgTab> last_tab_[2];
+    bool last_keep_all_[2] = {false, false};
 };
 
 }  // namespace vse

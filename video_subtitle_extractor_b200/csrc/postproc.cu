@@ -1,0 +1,424 @@
+// postproc.cu — device-side DB post-process, text-line crops and CTC greedy decode (sm_100a).
+//
+// Replaces, on the GPU, what paddleocr 2.10 does on the host between and after the two predictor runs
+// (reference call sites: backend/tools/ocr.py:27, backend/tools/subtitle_detect.py:24-26):
+//   cv2.findContours(pred > 0.3)  ->  union-find connected-component labelling (8-connectivity) + per-row extents
+//   get_mini_boxes / box_score_fast / unclip / filter_tag_det_res / sorted_boxes  ->  one block per component
+//   get_rotate_crop_image  ->  bicubic perspective gather;   CTCLabelDecode  ->  one block per text line.
+// The per-candidate arithmetic lives in dbpost_core.cuh / geom.cuh and is unit-tested on the CPU against cv2.
+// Compiled with --fmad=false: OpenCV's float code is not FMA-contracted and box corners must match bit for bit.
+//
+// Scope note: cv2.findContours(RETR_LIST) also reports hole borders; a hole contour only survives upstream when its
+// own box scores >= 0.6 and is >= 5 px after unclip.  Holes are not traced here (documented in DESIGN.md).
+#include "postproc.cuh"
+
+#include <cfloat>
+
+#include "dbpost_core.cuh"
+
+namespace vse {
+
+// ------------------------------------------------------------------------------------------------
+// connected components
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(volatile int* L, int a) {
+    int p = L[a];
+    while (p != a) {
+        a = p;
+        p = L[a];
+    }
+    return a;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) {
+            int old = atomicMin(&L[b], a);
+            done = (old == b);
+            b = old;
+        } else if (b < a) {
+            int old = atomicMin(&L[a], b);
+            done = (old == a);
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
+// block (32, 8): a warp covers 32 consecutive pixels of one row; the initial label is the start of the pixel's
+// run inside that 32-pixel segment (one ballot, no chains along rows)
+__global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ prob, const DetFrame* __restrict__ frames,
+                                                     float thresh, int* __restrict__ labels) {
+    const DetFrame fr = frames[blockIdx.z];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const bool in = x < fr.rw && y < fr.rh;
+    int g = 0;
+    bool fg = false;
+    if (in) {
+        g = fr.map_off + y * fr.rw + x;
+        fg = prob[g] > thresh;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, fg);
+    if (!in) return;
+    if (fg) {
+        const int lane = threadIdx.x;
+        const unsigned below = ~mask & ((1u << lane) - 1u);
+        const int start = below ? (32 - __clz(below)) : 0;
+        labels[g] = g - (lane - start);
+    } else {
+        labels[g] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict__ frames, int* labels) {
+    const DetFrame fr = frames[blockIdx.z];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.rw || y >= fr.rh) return;
+    const int g = fr.map_off + y * fr.rw + x;
+    if (labels[g] < 0) return;
+    const int rw = fr.rw;
+    const bool W = x > 0 && labels[g - 1] >= 0;
+    const bool up = y > 0;
+    const bool N = up && labels[g - rw] >= 0;
+    const bool NE = up && x + 1 < rw && labels[g - rw + 1] >= 0;
+    if (W) {
+        if (threadIdx.x == 0) uf_union(labels, g, g - 1);  // run continues across the 32-pixel segment boundary
+        if (!N && NE) uf_union(labels, g, g - rw + 1);
+    } else {
+        if (N) {
+            uf_union(labels, g, g - rw);
+        } else {
+            const bool NW = up && x > 0 && labels[g - rw - 1] >= 0;
+            if (NW) uf_union(labels, g, g - rw - 1);
+            if (NE) uf_union(labels, g, g - rw + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restrict__ frames, int* labels, int* slot_of,
+                                                        int* n_comp, int* roots, int* bbox) {
+    const int f = blockIdx.z;
+    const DetFrame fr = frames[f];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.rw || y >= fr.rh) return;
+    const int g = fr.map_off + y * fr.rw + x;
+    if (labels[g] < 0) return;
+    const int r = uf_find(labels, g);
+    labels[g] = r;
+    if (r == g) {
+        const int slot = atomicAdd(&n_comp[f], 1);
+        if (slot < kSlotCap) {
+            roots[f * kSlotCap + slot] = g;
+            slot_of[g] = slot;
+            int* b = bbox + (size_t(f) * kSlotCap + slot) * 4;
+            b[0] = x; b[1] = y; b[2] = x; b[3] = y;
+        } else {
+            slot_of[g] = -1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ frames, const int* __restrict__ labels,
+                                               const int* __restrict__ slot_of, int* bbox) {
+    const int f = blockIdx.z;
+    const DetFrame fr = frames[f];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fr.rw || y >= fr.rh) return;
+    const int g = fr.map_off + y * fr.rw + x;
+    const int r = labels[g];
+    if (r < 0) return;
+    const bool W = x > 0 && labels[g - 1] >= 0;
+    const bool E = x + 1 < fr.rw && labels[g + 1] >= 0;
+    if (W && E) return;
+    const int slot = slot_of[r];
+    if (slot < 0) return;
+    int* b = bbox + (size_t(f) * kSlotCap + slot) * 4;
+    if (!W) {
+        atomicMin(b + 0, x);
+        atomicMin(b + 1, y);
+        atomicMax(b + 3, y);
+    }
+    if (!E) atomicMax(b + 2, x);
+}
+
+// cv2.findContours(RETR_LIST) returns contours in reverse discovery order: descending root (raster) index
+__global__ void __launch_bounds__(256) db_sort_components(const int* __restrict__ n_comp, const int* __restrict__ roots,
+                                                          int* order, int* status) {
+    const int f = blockIdx.x;
+    int n = n_comp[f];
+    if (n > kSlotCap) {
+        if (threadIdx.x == 0) atomicOr(&status[f], 1);
+        n = kSlotCap;
+    }
+    const int* r = roots + size_t(f) * kSlotCap;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int mine = r[t];
+        int rank = 0;
+        for (int j = 0; j < n; j++) rank += r[j] > mine;
+        order[size_t(f) * kSlotCap + rank] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one block per component: row extents -> box -> score -> unclip -> frame-space quad
+// ------------------------------------------------------------------------------------------------
+static constexpr int kCandThreads = 128;
+static constexpr int kCandFields = 10;
+
+size_t db_candidate_smem_bytes(int max_rh) {
+    size_t rows = size_t(max_rh);
+    return rows * 2 * sizeof(int) + (2 * rows + 4) * sizeof(geom::P2i) + 5 * (2 * rows + 4) * sizeof(float) + 64;
+}
+
+__global__ void __launch_bounds__(kCandThreads) db_candidates(const float* __restrict__ prob, const DetFrame* __restrict__ frames,
+                                                              const int* __restrict__ labels, const int* __restrict__ n_comp,
+                                                              const int* __restrict__ roots, const int* __restrict__ bbox,
+                                                              const int* __restrict__ order, DbParams p, int max_rh, float* cand) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int* xl = reinterpret_cast<int*>(smem);
+    int* xr = xl + max_rh;
+    geom::P2i* hull = reinterpret_cast<geom::P2i*>(xr + max_rh);
+    float* work = reinterpret_cast<float*>(hull + 2 * max_rh + 4);
+    __shared__ dbpost::Candidate c;
+    __shared__ int win[4], qx[4], qy[4], ok;
+    __shared__ double wsum[kCandThreads / 32];
+    __shared__ int wcnt[kCandThreads / 32];
+
+    const int f = blockIdx.y;
+    const DetFrame fr = frames[f];
+    int n = min(n_comp[f], kSlotCap);
+    n = min(n, p.max_candidates);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int slot = order[size_t(f) * kSlotCap + k];
+        const int root = roots[size_t(f) * kSlotCap + slot];
+        const int* b = bbox + (size_t(f) * kSlotCap + slot) * 4;
+        const int xmin = b[0], ymin = b[1], xmax = b[2], ymax = b[3];
+        const int rows = ymax - ymin + 1;
+        // per-row extents of the component inside its bounding box
+        for (int r = warp; r < rows; r += kCandThreads / 32) {
+            const int* L = labels + fr.map_off + (ymin + r) * fr.rw;
+            int lo = INT_MAX, hi = -1;
+            for (int x0 = xmin; x0 <= xmax; x0 += 32) {
+                const int x = x0 + lane;
+                const bool hit = x <= xmax && L[x] == root;
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    lo = min(lo, x0 + __ffs(m) - 1);
+                    hi = max(hi, x0 + 31 - __clz(m));
+                }
+            }
+            if (lane == 0) { xl[r] = lo; xr[r] = hi; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ok = dbpost::stage1_component_box(xl, xr, rows, ymin, hull, work, 3.0f, &c) ? 1 : 0;
+            if (ok) dbpost::score_window(reinterpret_cast<const geom::P2f*>(c.box), fr.rw, fr.rh, win, qx, qy);
+        }
+        __syncthreads();
+        if (ok) {
+            // box_score_fast: mean of pred under fillPoly(quad) inside the clipped window (double accumulation)
+            const int ww = win[2] - win[0] + 1, wh = win[3] - win[1] + 1;
+            double s = 0.0;
+            int cnt = 0;
+            for (int y = warp; y < wh; y += kCandThreads / 32) {
+                int xa, xb;
+                if (!dbpost::quad_row_span(qx, qy, y, &xa, &xb)) continue;
+                xa = max(xa, 0);
+                xb = min(xb, ww - 1);
+                if (xa > xb) continue;
+                const float* row = prob + fr.map_off + (win[1] + y) * fr.rw + win[0];
+                float part = 0.f;
+                for (int x = xa + lane; x <= xb; x += 32) part += row[x];
+                s += (double)part;
+                if (lane == 0) cnt += xb - xa + 1;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) { wsum[warp] = s; wcnt[warp] = cnt; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                int tc = 0;
+                for (int w = 0; w < kCandThreads / 32; w++) { tot += wsum[w]; tc += wcnt[w]; }
+                c.score = tc > 0 ? (float)(tot / (double)tc) : 0.f;
+                if (p.box_thresh > c.score) ok = 0;
+                else ok = dbpost::stage3_unclip_scale(&c, p.unclip_ratio, 3.0f, fr.rw, fr.rh, fr.src_w, fr.src_h) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kCandFields) {
+            float* o = cand + (size_t(f) * p.max_candidates + k) * kCandFields;
+            float v;
+            if (threadIdx.x == 0) v = ok ? 1.f : 0.f;
+            else if (threadIdx.x == 1) v = c.score;
+            else v = c.quad[threadIdx.x - 2];
+            o[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// keep valid candidates in contour order, optionally re-order like TextSystem.sorted_boxes
+__global__ void db_compact(const int* __restrict__ n_comp, const float* __restrict__ cand, DbParams p, int* n_boxes,
+                           float* quads, float* scores, int* status) {
+    const int f = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    int n = min(min(n_comp[f], kSlotCap), p.max_candidates);
+    float* q = quads + size_t(f) * p.max_boxes * 8;
+    float* sc = scores + size_t(f) * p.max_boxes;
+    int m = 0;
+    for (int k = 0; k < n; k++) {
+        const float* c = cand + (size_t(f) * p.max_candidates + k) * kCandFields;
+        if (c[0] == 0.f) continue;
+        if (m >= p.max_boxes) {
+            atomicOr(&status[f], 2);
+            break;
+        }
+        sc[m] = c[1];
+        for (int i = 0; i < 8; i++) q[m * 8 + i] = c[2 + i];
+        m++;
+    }
+    if (p.sort_reading_order && m > 1) {
+        // sorted(dt_boxes, key=(y0, x0)) — stable
+        for (int i = 1; i < m; i++) {
+            float v[8], vs = sc[i];
+            for (int t = 0; t < 8; t++) v[t] = q[i * 8 + t];
+            int j = i - 1;
+            while (j >= 0 && (q[j * 8 + 1] > v[1] || (q[j * 8 + 1] == v[1] && q[j * 8] > v[0]))) {
+                for (int t = 0; t < 8; t++) q[(j + 1) * 8 + t] = q[j * 8 + t];
+                sc[j + 1] = sc[j];
+                j--;
+            }
+            for (int t = 0; t < 8; t++) q[(j + 1) * 8 + t] = v[t];
+            sc[j + 1] = vs;
+        }
+        // adjacent lines whose tops differ by < 10 px are ordered left to right
+        for (int i = 0; i < m - 1; i++) {
+            for (int j = i; j >= 0; j--) {
+                if (fabsf(q[(j + 1) * 8 + 1] - q[j * 8 + 1]) < 10.f && q[(j + 1) * 8] < q[j * 8]) {
+                    for (int t = 0; t < 8; t++) { float tmp = q[j * 8 + t]; q[j * 8 + t] = q[(j + 1) * 8 + t]; q[(j + 1) * 8 + t] = tmp; }
+                    float ts = sc[j]; sc[j] = sc[j + 1]; sc[j + 1] = ts;
+                } else {
+                    break;
+                }
+            }
+        }
+    }
+    n_boxes[f] = m;
+}
+
+void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const DetFrame* frames_host, int n_frames,
+                           int max_rh, int max_rw, const DbParams& p, const DbWorkspace& ws, cudaStream_t st,
+                           int64_t* launches) {
+    (void)frames_host;
+    if (n_frames <= 0) return;
+    cudaMemsetAsync(ws.n_comp, 0, sizeof(int) * n_frames, st);
+    cudaMemsetAsync(ws.status, 0, sizeof(int) * n_frames, st);
+    dim3 blk(32, 8), grid((max_rw + 31) / 32, (max_rh + 7) / 8, n_frames);
+    db_label_init<<<grid, blk, 0, st>>>(prob, frames_dev, p.thresh, ws.labels);
+    db_label_merge<<<grid, blk, 0, st>>>(frames_dev, ws.labels);
+    db_label_flatten<<<grid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox);
+    db_bbox<<<grid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.bbox);
+    db_sort_components<<<n_frames, 256, 0, st>>>(ws.n_comp, ws.roots, ws.order, ws.status);
+    size_t smem = db_candidate_smem_bytes(max_rh);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(db_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    db_candidates<<<dim3(16, n_frames), kCandThreads, smem, st>>>(prob, frames_dev, ws.labels, ws.n_comp, ws.roots, ws.bbox,
+                                                                  ws.order, p, max_rh, ws.cand);
+    db_compact<<<n_frames, 32, 0, st>>>(ws.n_comp, ws.cand, p, ws.n_boxes, ws.quads, ws.scores, ws.status);
+    if (launches) *launches += 7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// crops
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) crop_warp_kernel(const CropJob* __restrict__ jobs, const short* __restrict__ tab,
+                                                        uint8_t* __restrict__ dst) {
+    const CropJob& j = jobs[blockIdx.y];
+    const int ow = j.rot90 ? j.ch : j.cw, oh = j.rot90 ? j.cw : j.ch;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ow * oh) return;
+    const int oy = idx / ow, ox = idx - oy * ow;
+    // np.rot90(a)[i][j] = a[j][W - 1 - i]
+    const int x = j.rot90 ? (j.cw - 1 - oy) : ox;
+    const int y = j.rot90 ? ox : oy;
+    unsigned char px[3];
+    dbpost::warp_cubic_pixel(j.frame, j.fh, j.fw, j.stride, j.pix, j.M, tab, x, y, px);
+    reinterpret_cast<uchar4*>(dst)[j.dst_off + idx] = make_uchar4(px[0], px[1], px[2], 0);
+}
+
+void launch_crops(const CropJob* jobs_dev, int n_jobs, int max_pix, const short* cubic_tab, uint8_t* dst, cudaStream_t st) {
+    if (n_jobs <= 0 || max_pix <= 0) return;
+    dim3 grid((max_pix + 255) / 256, n_jobs);
+    crop_warp_kernel<<<grid, 256, 0, st>>>(jobs_dev, cubic_tab, dst);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTC greedy decode: argmax/max per time step, collapse repeats, drop blank (0), mean of kept max-probs
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict__ probs, int C, const int* __restrict__ toff,
+                                                         const int* __restrict__ tlen, int max_t, int* __restrict__ ids,
+                                                         int* __restrict__ id_len, float* __restrict__ score) {
+    extern __shared__ __align__(8) unsigned char sm[];
+    int* bi = reinterpret_cast<int*>(sm);
+    float* bp = reinterpret_cast<float*>(bi + max_t);
+    const int n = blockIdx.x;
+    const int T = tlen[n];
+    const float* base = probs + size_t(toff[n]) * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = warp; t < T; t += 4) {
+        const float* row = base + size_t(t) * C;
+        float best = -FLT_MAX;
+        int idx = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float v = row[c];
+            if (v > best) { best = v; idx = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+        }
+        if (lane == 0) { bi[t] = idx; bp[t] = best; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int m = 0;
+        float s = 0.f;
+        int prev = -1;
+        for (int t = 0; t < T; t++) {
+            const int i = bi[t];
+            if (i != prev && i != 0) {
+                ids[size_t(n) * max_t + m] = i;
+                s += bp[t];
+                m++;
+            }
+            prev = i;
+        }
+        id_len[n] = m;
+        score[n] = m > 0 ? s / float(m) : 0.f;
+    }
+}
+
+void launch_ctc_decode(const float* probs, int C, const int* toff, const int* tlen, int n, int max_t, int* ids, int* id_len,
+                       float* score, cudaStream_t st) {
+    if (n <= 0) return;
+    size_t smem = size_t(max_t) * 8;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaFuncSetAttribute(ctc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    ctc_decode_kernel<<<n, 128, smem, st>>>(probs, C, toff, tlen, max_t, ids, id_len, score);
+}
+
+}  // namespace vse
