@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — OCR frames/s (det + rec) of the B200 engine on BASELINE.json configs[1]:
+synthetic 1080p subtitle frames, batch = 32 frames per vse_run call, V4/ch_det_fast + V4/en_rec_fast.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path (vse_run: det pre-process, det net, DB post-process, crops, rec net, CTC decode)
+over one batch of 32 frames per GPU.  `value` times the steps with the frames already resident in HBM; `e2e` times the
+same call with the frames in pinned HOST memory (H2D of the frames and D2H of the results inside the timed region).
+Weak scaling: every rank owns its own contiguous 32-frame range of each global batch (no collective on the hot path;
+one NCCL broadcast of the packed plans at start-up).  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/: torch-CPU fp32 graph arithmetic + cv2
+host logic, one frame per call, det batch 1, rec batches of <= 6 — exactly how the reference drives paddleocr) on the
+host cores.  The reference's own Paddle runtime is a pip dependency that is absent from this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DET, REC = "V4/ch_det_fast", "V4/en_rec_fast"
+METRIC = "ocr_frames_per_sec_det_rec"
+UNIT = "frames/s"
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per vse_run call per GPU")
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--pool", type=int, default=3, help="distinct batches cycled through (3 x 32 x 6.2 MB > L2)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm (oracle) — used by `--impl reference` and by the cpu_baseline leg
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle(det_blob, rec_blob):
+    import torch
+    from oracle.pipeline import OraclePipeline      # checker / CPU baseline only
+    torch.set_num_threads(os.cpu_count() or 1)
+    return OraclePipeline.from_plans(det_blob, rec_blob), torch.get_num_threads()
+
+
+def time_cpu(oracle, frames, budget_s):
+    """frames/s of the CPU restatement on as many of `frames` as fit the budget (at least 2, first one is warm-up)."""
+    oracle.ocr(frames[0])
+    t0 = time.perf_counter()
+    n = 0
+    for f in frames:
+        oracle.ocr(f)
+        n += 1
+        if time.perf_counter() - t0 > budget_s and n >= 2:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from video_subtitle_extractor_b200 import weights
+    from video_subtitle_extractor_b200.synth import SynthStream
+    det_blob, rec_blob = weights.load_plan_blob(DET), weights.load_plan_blob(REC)
+    oracle, cores = cpu_oracle(det_blob, rec_blob)
+    per_step = 4                                     # bounded sample of the 32-frame batch per step
+    stream = SynthStream(args.height, args.width)
+    frames = [stream.frame(i * 7) for i in range(per_step * 2)]
+    for _ in range(max(args.warmup, 1)):
+        oracle.ocr(frames[0])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for k in range(per_step):
+            oracle.ocr(frames[(s * per_step + k) % len(frames)])
+    dt = time.perf_counter() - t0
+    fps = args.steps * per_step / dt
+    sample = f"{per_step} of the {args.batch} frames of each step ({args.height}x{args.width}), one frame per call, rec batches <= 6"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.height}p subtitle frames, {DET} + {REC}, CPU restatement of the reference path",
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def step_roofline(eng, E):
+    """Per-kernel achieved HBM GB/s of the dominant kernel, from CUDA events between plan steps (engine stream)."""
+    from video_subtitle_extractor_b200 import plan as P
+    rows = []
+    for which in (E.PLAN_DET, E.PLAN_REC):
+        try:
+            ms, info = eng.debug_time_steps(which, reps=5)
+        except RuntimeError:
+            continue
+        for t, i in zip(ms, info):
+            op, pin, pout, cin, cout, taps, eb_in, eb_out = (int(v) for v in i)
+            pad8 = lambda c: (c + 7) // 8 * 8
+            wbytes = taps * cin * cout * 4 if op in (P.OP_CONV, P.OP_STEM) else taps * cin * 4
+            if op == P.OP_STEM:
+                bytes_ = pin * 4 + pout * pad8(cout) * eb_out + wbytes
+            elif op in (P.OP_CONV, P.OP_DWCONV, P.OP_DECONV2):
+                bytes_ = pin * pad8(cin) * eb_in + pout * (cout if eb_out == 4 else pad8(cout)) * eb_out + wbytes
+            else:
+                bytes_ = pin * pad8(cin) * eb_in + pout * pad8(cout) * eb_out
+            flops = 2 * pout * cin * cout * taps if op in (P.OP_CONV, P.OP_STEM, P.OP_DECONV2) else 0
+            rows.append((which, P.OP_NAMES[op], float(t), bytes_, flops))
+    if not rows:
+        return None, []
+    by_kernel = {}
+    for which, name, t, b, f in rows:
+        k = "conv_simt_kernel" if name in ("CONV", "STEM") else name.lower() + "_kernel"
+        a = by_kernel.setdefault(k, [0.0, 0, 0, 0])
+        a[0] += t; a[1] += b; a[2] += f; a[3] += 1
+    top = max(by_kernel.items(), key=lambda kv: kv[1][0])
+    return top, sorted(((k, v[0], v[1], v[2], v[3]) for k, v in by_kernel.items()), key=lambda r: -r[1])
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            for key in ("hbm_gbs", "hbm_gbps", "hbm_gb_s"):
+                if key in d:
+                    return float(d[key]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f)
+        except Exception:
+            return None
+    return None
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+    from video_subtitle_extractor_b200 import engine as E
+    from video_subtitle_extractor_b200 import shard, weights
+    from video_subtitle_extractor_b200.synth import SynthStream
+
+    if E.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    # one-time plan broadcast (rank 0 reads the packed plans; NCCL over NVLink)
+    blobs = [weights.load_plan_blob(DET), weights.load_plan_blob(REC)] if rank == 0 else None
+    det_blob, rec_blob = shard.broadcast_blobs(blobs, 0, dev) if world > 1 else blobs
+
+    B, H, W = args.batch, args.height, args.width
+    stream = SynthStream(H, W)
+    # rank r owns frames [r*B, (r+1)*B) of every global batch of world*B frames
+    host_batches, dev_batches = [], []
+    for p in range(args.pool):
+        lo, hi = shard.frame_range(rank, world, world * B)
+        idx = [p * world * B + k for k in range(lo, hi)]
+        pinned = torch.empty((len(idx), H, W, 3), dtype=torch.uint8, pin_memory=True)
+        arr = pinned.numpy()
+        for j, i in enumerate(idx):
+            arr[j] = stream.frame(i)
+        host_batches.append(pinned)
+        dev_batches.append(pinned.to(dev))
+    torch.cuda.synchronize()
+
+    eng = E.Engine(device=local_rank, precision=E.PRECISION_FP16)
+    eng.load_plan(E.PLAN_DET, det_blob, DET)
+    eng.load_plan(E.PLAN_REC, rec_blob, REC)
+    hs, ws = [H] * B, [W] * B
+    frame_bytes = H * W * 3
+
+    def step(batches, k, mem_kind):
+        t = batches[k % len(batches)]
+        base = t.data_ptr()
+        return eng.run_device([base + j * frame_bytes for j in range(B)], hs, ws, None, mem_kind=mem_kind)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, mem_kind):
+        for k in range(args.warmup):
+            step(batches, k, mem_kind)
+        barrier()
+        dev_ms = 0.0
+        l0 = eng.launch_count
+        t0 = time.perf_counter()
+        n_lines = 0
+        for k in range(args.steps):
+            res = step(batches, k, mem_kind)
+            dev_ms += float(eng.last_timings[7])
+            n_lines += sum(len(r.quads) for r in res)
+        barrier()
+        wall = time.perf_counter() - t0
+        return wall, dev_ms / 1e3, eng.launch_count - l0, n_lines, res
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    wall, dev_s, launches, n_lines, last = timed(dev_batches, E.MEM_DEVICE)
+    clocks = sampler.stop()
+    wall_e2e, dev_s_e2e, _, _, last_e2e = timed(host_batches, E.MEM_PINNED)
+    stage_ms = [float(x) for x in eng.last_timings]
+
+    wall_max = shard.max_over_ranks(wall, dev)
+    wall_e2e_max = shard.max_over_ranks(wall_e2e, dev)
+    total_frames = world * B * args.steps
+    value = total_frames / wall_max
+    e2e_value = total_frames / wall_e2e_max
+    d2h = sum(4 + len(r.quads) * (32 + 4 + 4 + 4 + 4) + sum(len(i) for i in r.ids) * 4 for r in last_e2e)
+
+    out = None
+    if rank == 0:
+        step(dev_batches, 0, E.MEM_DEVICE)    # make the last run of both plans a full resident batch
+        top, table = step_roofline(eng, E)
+        peak, peak_src = hbm_peak()
+        roofline = None
+        if top is not None:
+            name, (t_ms, bytes_, flops, n_launch) = top
+            achieved = bytes_ / (t_ms * 1e-3) / 1e9
+            traffic = ncu_traffic()
+            roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                        "peak_source": peak_src, "launches_per_step": n_launch,
+                        "algorithmic_bytes_per_launch": bytes_ / n_launch, "avg_launch_ms": t_ms / n_launch,
+                        "tflops": flops / (t_ms * 1e-3) / 1e12,
+                        "per_kernel_ms": {k: round(t, 4) for k, t, _, _, _ in table}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            oracle, cores = cpu_oracle(det_blob, rec_blob)
+            frames = [host_batches[0].numpy()[j] for j in range(min(B, 16))]
+            fps, n, dt = time_cpu(oracle, frames, args.cpu_seconds)
+            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n} of the {B} frames of one step ({H}x{W}) in {dt:.1f} s: CPU restatement of the reference "
+                             f"path (torch-CPU fp32 + cv2), one frame per call, rec batches <= 6"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"synthetic {H}p subtitle frames (SURVEY.md §8d generator), {DET} + {REC}",
+                       "frames_per_step_per_gpu": B, "global_frames_per_step": world * B, "frame": [H, W, 3],
+                       "parallelism": f"frame-range sharding x{world}", "text_lines_per_step": n_lines / max(args.steps, 1),
+                       "l2": f"inputs larger than L2: {args.pool} distinct batches x {B * frame_bytes / 1e6:.0f} MB cycled",
+                       "precision": "fp16 activations, fp32 accumulate"},
+            "device_ms_per_step": dev_s / args.steps * 1e3, "stage_ms_last_e2e_step": stage_ms,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": wall_e2e_max / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+    eng.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = env_rank()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,11 @@ int  vse_debug_db_postprocess(vse_engine* e, const float* prob, int32_t rh, int3
 int  vse_debug_crop(vse_engine* e, const uint8_t* frame, int32_t h, int32_t w, const float* quad,
                     uint8_t* out_bgr, int32_t capacity, int32_t* out_h, int32_t* out_w);
 
+/* Re-runs the steps of the last run of plan `which` with a CUDA event between steps (on the engine's stream);
+ * ms[k] = mean device time of step k; info[k][8] = {op, in_pixels, out_pixels, cin, cout, taps, in_elt_bytes,
+ * out_elt_bytes}.  Returns the number of steps.  bench.py derives the per-kernel roofline from this. */
+int  vse_debug_time_steps(vse_engine* e, int32_t which, int32_t reps, float* ms, int64_t* info, int32_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,13 +40,31 @@ class PlanInterpreter:
 
     def __init__(self, plan: P.Plan):
         self.plan = plan
+        # weights converted once to the layouts torch wants (keeps the CPU baseline honest: no per-call re-layout)
+        self._wcache: Dict[int, Dict[str, torch.Tensor]] = {}
+        for k, s in enumerate(plan.steps):
+            c: Dict[str, torch.Tensor] = {}
+            for name, arr in s.w.items():
+                c[name] = torch.from_numpy(np.array(arr, dtype=np.float32, copy=True))
+            if s.op in (P.OP_CONV, P.OP_STEM):
+                c["weight"] = c["weight"].permute(0, 3, 1, 2).contiguous()
+            elif s.op == P.OP_DWCONV:
+                c["weight"] = c["weight"].permute(2, 0, 1).unsqueeze(1).contiguous()
+            elif s.op == P.OP_DECONV2:
+                c["weight"] = c["weight"].permute(3, 2, 0, 1).contiguous()
+            elif s.op == P.OP_VECLIN:
+                c["weight"] = c["weight"].t().contiguous()
+            self._wcache[id(s)] = c
+
+    def _w(self, s: P.Step, name: str) -> torch.Tensor:
+        return self._wcache[id(s)][name]
 
     def _epilogue(self, s: P.Step, y: torch.Tensor, env) -> torch.Tensor:
         shp = [1, -1, 1, 1] if y.dim() == 4 else [1, -1]
-        y = y + torch.from_numpy(s.w["bias"]).reshape(shp)
+        y = y + self._w(s, "bias").reshape(shp)
         y = _act(y, s.p["act"], s.p.get("hs_slope", 0.0), s.p.get("hs_offset", 0.0))
         if s.p.get("has_post"):
-            y = y * torch.from_numpy(s.w["post_scale"]).reshape(shp) + torch.from_numpy(s.w["post_shift"]).reshape(shp)
+            y = y * self._w(s, "post_scale").reshape(shp) + self._w(s, "post_shift").reshape(shp)
         if s.p.get("has_res"):
             y = y + env[s.ins[1]]
         return _act(y, s.p.get("act2", P.ACT_NONE))
@@ -85,19 +103,19 @@ class PlanInterpreter:
                 materialise(v)
             op = s.op
             if op in (P.OP_CONV, P.OP_STEM):
-                w = torch.from_numpy(s.w["weight"]).permute(0, 3, 1, 2).contiguous()
+                w = self._w(s, "weight")
                 y = F.conv2d(env[s.ins[0]], w, None, (s.p["sh"], s.p["sw"]), (s.p["ph"], s.p["pw"]))
                 put(s.out, self._epilogue(s, y, env))
             elif op == P.OP_DWCONV:
-                w = torch.from_numpy(s.w["weight"]).permute(2, 0, 1).unsqueeze(1).contiguous()
+                w = self._w(s, "weight")
                 y = F.conv2d(env[s.ins[0]], w, None, (s.p["sh"], s.p["sw"]), (s.p["ph"], s.p["pw"]), 1, w.shape[0])
                 put(s.out, self._epilogue(s, y, env))
             elif op == P.OP_DECONV2:
-                w = torch.from_numpy(s.w["weight"]).permute(3, 2, 0, 1).contiguous()  # [cin,cout,kh,kw]
+                w = self._w(s, "weight")  # [cin,cout,kh,kw]
                 y = F.conv_transpose2d(env[s.ins[0]], w, None, 2)
                 put(s.out, self._epilogue(s, y, env))
             elif op == P.OP_VECLIN:
-                y = env[s.ins[0]] @ torch.from_numpy(s.w["weight"]).t()
+                y = env[s.ins[0]] @ self._w(s, "weight")
                 put(s.out, self._epilogue(s, y, env))
             elif op == P.OP_GPOOL:
                 put(s.out, env[s.ins[0]].mean(dim=(2, 3)))
@@ -126,12 +144,11 @@ class PlanInterpreter:
             elif op == P.OP_ELTWISE:
                 xx = env[s.ins[0]]
                 shp = [1, -1, 1, 1] if xx.dim() == 4 else [1, -1]
-                y = xx * torch.from_numpy(s.w["scale"]).reshape(shp) + torch.from_numpy(s.w["shift"]).reshape(shp)
+                y = xx * self._w(s, "scale").reshape(shp) + self._w(s, "shift").reshape(shp)
                 put(s.out, _act(y, s.p["act"], s.p.get("hs_slope", 0.0), s.p.get("hs_offset", 0.0)))
             elif op == P.OP_LAYERNORM:
                 xx = env[s.ins[0]]  # [B,C,1,T]
-                y = F.layer_norm(xx.permute(0, 2, 3, 1), [xx.shape[1]], torch.from_numpy(s.w["gamma"]),
-                                 torch.from_numpy(s.w["beta"]), s.p["eps"])
+                y = F.layer_norm(xx.permute(0, 2, 3, 1), [xx.shape[1]], self._w(s, "gamma"), self._w(s, "beta"), s.p["eps"])
                 put(s.out, y.permute(0, 3, 1, 2).contiguous())
             elif op == P.OP_ATTN:
                 qkv = env[s.ins[0]]  # [B, 3*H*D, 1, T]
@@ -164,8 +181,7 @@ class PlanInterpreter:
             outs = []
             for d in range(ndir):
                 k = l * ndir + d
-                w_ih, w_hh, b = (torch.from_numpy(s.w[f"w_ih{k}"]), torch.from_numpy(s.w[f"w_hh{k}"]),
-                                 torch.from_numpy(s.w[f"b{k}"]))
+                w_ih, w_hh, b = self._w(s, f"w_ih{k}"), self._w(s, f"w_hh{k}"), self._w(s, f"b{k}")
                 inp = seq.flip(0) if d == 1 else seq
                 T, B, _ = inp.shape
                 h = torch.zeros(B, hidden)

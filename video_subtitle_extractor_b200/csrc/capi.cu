@@ -142,4 +142,11 @@ int vse_debug_crop(vse_engine* e, const uint8_t* frame, int32_t h, int32_t w, co
     return guarded(e, [&] { e->impl->debug_crop(frame, h, w, quad, out_bgr, capacity, out_h, out_w); });
 }
 
+int vse_debug_time_steps(vse_engine* e, int32_t which, int32_t reps, float* ms, int64_t* info, int32_t capacity) {
+    if (!e || !ms || !info) return VSE_ERR_INVALID;
+    int n = 0;
+    int rc = guarded(e, [&] { n = e->impl->time_steps(which, reps, ms, info, capacity); });
+    return rc == VSE_OK ? n : rc;
+}
+
 }  // extern "C"

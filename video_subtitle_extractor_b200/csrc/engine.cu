@@ -420,7 +420,7 @@ void Engine::run_plan(int which, const std::vector<ImgTab>& in_tab, const uint8_
     exec_steps(which);
 }
 
-void Engine::exec_steps(int which) {
+void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
     LoadedPlan& lp = plans_[which];
     const PlanData& pd = lp.data;
     ExecContext& cx = ctx_[which];
@@ -448,7 +448,9 @@ void Engine::exec_steps(int which) {
             e.res_cs = value_cs(pd, s.ins[1]);
         }
     };
+    if (step_events) cudaEventRecord((*step_events)[0], stream);
     for (size_t k = 0; k < pd.steps.size(); k++) {
+        if (step_events && k > 0) cudaEventRecord((*step_events)[k], stream);
         const StepRec& s = pd.steps[k];
         const StepDev& d = lp.dev[k];
         const ValueRec& vo = pd.values[s.out];
@@ -577,7 +579,54 @@ void Engine::exec_steps(int which) {
                 throw InvalidArg{std::string("unsupported step ") + kOpNames[s.op]};
         }
     }
+    if (step_events) cudaEventRecord((*step_events)[pd.steps.size()], stream);
     VSE_CUDA(cudaGetLastError());
+}
+
+// Re-executes the steps of the last run of plan `which` (same buffers, same geometry) with a CUDA event between
+// consecutive steps; ms[k] = mean device time of step k over `reps` runs.  info[k] = {op, in_pixels, out_pixels,
+// cin, cout, kh*kw, act_bytes, out_elt_bytes} lets the caller compute each step's algorithmic bytes / FLOPs.
+int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
+    if (which < 0 || which > 1 || !plans_[which].loaded || last_tab_[which].empty()) throw StateError{"no previous run of this plan"};
+    const PlanData& pd = plans_[which].data;
+    const int n = int(pd.steps.size());
+    if (cap < n) throw CapacityError{"time_steps: capacity too small"};
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) VSE_CUDA(cudaEventCreate(&e));
+    std::vector<double> acc(n, 0.0);
+    exec_steps(which);  // warm
+    VSE_CUDA(cudaStreamSynchronize(stream));
+    for (int r = 0; r < reps; r++) {
+        exec_steps(which, &ev);
+        VSE_CUDA(cudaStreamSynchronize(stream));
+        for (int k = 0; k < n; k++) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+            acc[k] += t;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    const ExecContext& cx = ctx_[which];
+    for (int k = 0; k < n; k++) {
+        ms[k] = float(acc[k] / std::max(reps, 1));
+        const StepRec& s = pd.steps[k];
+        auto pixels = [&](int vid) -> int64_t {
+            if (vid < 0) return 0;
+            if (pd.values[vid].kind == KIND_VEC) return cx.n_img;
+            int g = cx.vals[vid].geo;
+            return g >= 0 ? cx.geos[g].total : 0;
+        };
+        int64_t* o = info + size_t(k) * 8;
+        o[0] = s.op;
+        o[1] = pixels(s.ins[0]);
+        o[2] = pixels(s.out);
+        o[3] = s.ins[0] >= 0 ? pd.values[s.ins[0]].channels : 0;
+        o[4] = pd.values[s.out].channels;
+        o[5] = (s.op == OP_CONV || s.op == OP_STEM || s.op == OP_DWCONV) ? s.p[P_KH] * s.p[P_KW] : (s.op == OP_DECONV2 ? 4 : 1);
+        o[6] = s.ins[0] >= 0 ? int64_t(elt_size(pd.values[s.ins[0]])) : 0;
+        o[7] = int64_t(elt_size(pd.values[s.out]));
+    }
+    return n;
 }
 
 void Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {

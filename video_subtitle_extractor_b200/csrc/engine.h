@@ -137,6 +137,7 @@ class Engine {
                     int mem_kind, vse_result* out, bool det_only);
 
     // debug hooks
+    int time_steps(int which, int reps, float* ms, int64_t* info, int cap);
     void debug_run_plan(int which, const uint8_t* const* images, int n, int h, const int32_t* w, const int32_t* valid_w,
                         bool keep_all);
     void debug_resize(const uint8_t* src, int sh, int sw, int stride, uint8_t* dst, int dh, int dw);
@@ -158,7 +159,7 @@ class Engine {
   private:
     void prepare_plan(LoadedPlan& lp);
     void build_context(int which, const std::vector<ImgTab>& in_tab, bool keep_all);
-    void exec_steps(int which);
+    void exec_steps(int which, std::vector<cudaEvent_t>* step_events = nullptr);
     size_t elt_size(const ValueRec& v) const;
     int value_cs(const PlanData& pd, int vid) const;  // channel stride in elements
     void* vptr(int which, int vid) const;

@@ -36,7 +36,7 @@ class VseResult(C.Structure):
 
 EXPORTS = ["vse_default_config", "vse_abi_version", "vse_device_count", "vse_create", "vse_destroy", "vse_last_error",
            "vse_load_plan", "vse_run", "vse_det_only", "vse_launch_count", "vse_debug_run_plan", "vse_debug_get_value",
-           "vse_debug_resize_bilinear", "vse_debug_db_postprocess", "vse_debug_crop"]
+           "vse_debug_resize_bilinear", "vse_debug_db_postprocess", "vse_debug_crop", "vse_debug_time_steps"]
 
 
 def load_library(path: Optional[str] = None):
@@ -72,6 +72,7 @@ def load_library(path: Optional[str] = None):
     lib.vse_debug_resize_bilinear.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32]
     lib.vse_debug_db_postprocess.argtypes = [vp, p_f32, i32, i32, i32, i32, p_f32, p_f32, i32, p_i32]
     lib.vse_debug_crop.argtypes = [vp, vp, i32, i32, p_f32, vp, i32, p_i32, p_i32]
+    lib.vse_debug_time_steps.argtypes = [vp, i32, i32, p_f32, C.POINTER(C.c_int64), i32]
     _lib = lib
     return lib
 
@@ -214,6 +215,16 @@ class Engine:
         n2 = self.lib.vse_debug_get_value(self._h, which, vid, out.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(ch))
         self._check(n2, "vse_debug_get_value")
         return out.reshape(-1, ch.value)
+
+    def debug_time_steps(self, which: int, reps: int = 5):
+        """-> (ms per step, info[n,8]) for the last run of plan `which` (see include/vse_b200.h)."""
+        cap = 1024
+        ms = np.zeros(cap, np.float32)
+        info = np.zeros((cap, 8), np.int64)
+        n = self.lib.vse_debug_time_steps(self._h, which, reps, ms.ctypes.data_as(C.POINTER(C.c_float)),
+                                          info.ctypes.data_as(C.POINTER(C.c_int64)), cap)
+        self._check(n, "vse_debug_time_steps")
+        return ms[:n].copy(), info[:n].copy()
 
     def debug_resize(self, img_bgr: np.ndarray, dh: int, dw: int) -> np.ndarray:
         img = np.ascontiguousarray(img_bgr, dtype=np.uint8)
