@@ -45,6 +45,7 @@ typedef enum {
 enum { VSE_MEM_HOST = 0, VSE_MEM_PINNED = 1, VSE_MEM_DEVICE = 2 };
 enum { VSE_PLAN_DET = 0, VSE_PLAN_REC = 1 };
 enum { VSE_PRECISION_FP16 = 0, VSE_PRECISION_FP32 = 1 };
+enum { VSE_FLAG_NO_TENSOR_CORES = 1 };  /* vse_config.flags: keep every conv on the CUDA-core kernels (A/B checks) */
 
 /* Mirrors the knobs the reference passes to PaddleOCR / TextDetector (ocr.py:91-113) and the
  * upstream defaults it relies on (utility.parse_args(): SURVEY.md Appendix D.8 item 3). */
@@ -60,7 +61,7 @@ typedef struct {
     int32_t rec_image_w;         /* 320                                           */
     int32_t rec_batch_num;       /* 6   (config.recBatchNumber, ocr.py:99)        */
     int32_t max_boxes_per_frame; /* device-side candidate capacity per frame      */
-    int32_t flags;               /* reserved, 0                                   */
+    int32_t flags;               /* VSE_FLAG_* bits                               */
 } vse_config;
 
 /* Results, caller-allocated.  Boxes of frame f occupy rows [sum(n_boxes[0..f)), +n_boxes[f]). */
@@ -100,6 +101,8 @@ int  vse_det_only(vse_engine* e, const uint8_t* const* frames, const int32_t* h,
 
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 int64_t vse_launch_count(const vse_engine* e);
+/* ... of which launches of the tcgen05/TMA implicit-GEMM kernel (gemm_tc.cu). */
+int64_t vse_tc_launch_count(const vse_engine* e);
 
 /* ---- test / profiling hooks (used by tests/ and bench.py only) --------------------------- */
 

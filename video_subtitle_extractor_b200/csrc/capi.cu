@@ -111,6 +111,8 @@ int vse_det_only(vse_engine* e, const uint8_t* const* frames, const int32_t* h, 
 
 int64_t vse_launch_count(const vse_engine* e) { return e ? e->impl->launches : 0; }
 
+int64_t vse_tc_launch_count(const vse_engine* e) { return e ? e->impl->tc_launches : 0; }
+
 int vse_debug_run_plan(vse_engine* e, int32_t which, const uint8_t* const* images, int32_t n, int32_t h, const int32_t* w,
                        const int32_t* valid_w, int32_t keep_all) {
     if (!e || !images || !w || n <= 0) return VSE_ERR_INVALID;

@@ -19,6 +19,11 @@ Engine::Engine(const vse_config& c) : cfg(c) {
     if (cfg.device < 0 || cfg.device >= ndev) throw InvalidArg{"device ordinal out of range"};
     VSE_CUDA(cudaSetDevice(cfg.device));
     VSE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop{};
+    VSE_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+    sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) throw CudaError{"this engine is built for sm_100a (B200); found compute capability " +
+                                          std::to_string(prop.major) + "." + std::to_string(prop.minor)};
 }
 
 size_t Engine::elt_size(const ValueRec& v) const {
@@ -153,6 +158,26 @@ void Engine::prepare_plan(LoadedPlan& lp) {
     }
     lp.weights.reserve(host.size() * sizeof(float));
     VSE_CUDA(cudaMemcpy(lp.weights.p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // fp16 K-major weight matrices for the tensor-core path
+    lp.tcw.assign(pd.steps.size(), TcWeights{});
+    lp.tcw_off.assign(pd.steps.size(), 0);
+    if (cfg.precision == VSE_PRECISION_FP16 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
+        std::vector<uint16_t> all;
+        for (size_t k = 0; k < pd.steps.size(); k++) {
+            const StepRec& s = pd.steps[k];
+            if (s.op != OP_CONV || s.p[P_SH] != 1 || s.p[P_SW] != 1) continue;
+            lp.tcw[k] = tc_pack_weights(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], s.p[P_KH] * s.p[P_KW]);
+            while (all.size() % 512) all.push_back(0);   // 1024-byte aligned matrices
+            lp.tcw_off[k] = all.size() * sizeof(uint16_t);
+            all.insert(all.end(), lp.tcw[k].b.begin(), lp.tcw[k].b.end());
+            lp.tcw[k].b.clear();
+            lp.tcw[k].b.shrink_to_fit();
+        }
+        if (!all.empty()) {
+            lp.tc_weights.reserve(all.size() * sizeof(uint16_t));
+            VSE_CUDA(cudaMemcpy(lp.tc_weights.p, all.data(), all.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        }
+    }
     const float* base = lp.weights.as<float>();
     auto ptr = [&](size_t off) -> const float* { return off == SIZE_MAX ? nullptr : base + off; };
     for (size_t k = 0; k < pd.steps.size(); k++) {
@@ -206,6 +231,8 @@ static Geo scale_geo(const Geo& in, int scale) {
     g.total = off;
     return g;
 }
+
+static inline bool keep_all_disables_tc(bool) { return false; }
 
 static bool same_geo(const Geo& a, const Geo& b) {
     if (a.tab.size() != b.tab.size()) return false;
@@ -378,6 +405,25 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
     cx.scratch_bytes = scratch;
     cx.arena_bytes = cx.scratch_off + scratch + 256;
     arena_[which].reserve(cx.arena_bytes);
+
+    // tensor-core plans (need the final arena addresses for the TMA descriptors)
+    cx.tc.assign(pd.steps.size(), TcConv{});
+    for (size_t k = 0; k < pd.steps.size() && !keep_all_disables_tc(keep_all); k++) {
+        const StepRec& s = pd.steps[k];
+        if (s.op != OP_CONV || lp.tcw[k].n_chunk == 0) continue;
+        const ValueRec& vo = pd.values[s.out];
+        if (vo.dtype == DT_F32 || s.ins[0] == pd.hdr.input_vid) continue;
+        const int kh = s.p[P_KH], kw = s.p[P_KW], ph = s.p[P_PH], pw = s.p[P_PW];
+        const Geo& gi = cx.geos[cx.vals[s.ins[0]].geo];
+        const bool flat = kh == 1 && kw == 1 && ph == 0 && pw == 0;
+        bool uniform = true;
+        for (auto& t : gi.tab) uniform = uniform && t.h == gi.tab[0].h && t.w == gi.tab[0].w;
+        if (!flat && !(uniform && 2 * ph == kh - 1 && 2 * pw == kw - 1)) continue;
+        const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_off[k];
+        std::string why = tc_conv_setup(cx.tc[k], vptr(which, s.ins[0]), value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], flat,
+                                        gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw);
+        if (!why.empty()) cx.tc[k].valid = false;
+    }
 }
 
 void* Engine::vptr(int which, int vid) const {
@@ -630,8 +676,16 @@ int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
 }
 
 void Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
-    (void)which;
-    (void)step;
+    TcConv& t = ctx_[which].tc[step];
+    if (prec == 0 && t.valid) {
+        t.out = a.out;
+        t.out_cs = a.out_cs;
+        t.n_store = a.cout_store;
+        t.epi = a.epi;
+        launch_conv_tc(t, sm_count, stream);
+        tc_launches++;
+        return;
+    }
     launch_conv_simt(a, prec, stream);
 }
 

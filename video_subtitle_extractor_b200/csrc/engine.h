@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/vse_b200.h"
+#include "gemm_tc.h"
 #include "nn_kernels.h"
 #include "plan.h"
 #include "postproc.cuh"
@@ -108,6 +109,10 @@ struct LoadedPlan {
     PlanData data;
     std::vector<StepDev> dev;
     DevBuf weights;  // all device parameters
+    // tensor-core path: fp16 K-major weight matrices of the CONV steps (gemm_tc.cu)
+    std::vector<TcWeights> tcw;      // per step (b emptied after upload; n_chunk == 0 => not packed)
+    std::vector<size_t> tcw_off;     // byte offset into tc_weights
+    DevBuf tc_weights;
     bool loaded = false;
 };
 
@@ -119,6 +124,7 @@ struct ExecContext {
     size_t arena_bytes = 0;
     size_t scratch_off = 0, scratch_bytes = 0;
     int n_img = 0;
+    std::vector<TcConv> tc;   // per step; valid => the step runs on the tcgen05 kernel for this geometry
 };
 
 class Engine {
@@ -155,6 +161,8 @@ class Engine {
     int64_t launches = 0;
     vse_config cfg;
     cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int64_t tc_launches = 0;
 
   private:
     void prepare_plan(LoadedPlan& lp);

@@ -1,0 +1,457 @@
+// gemm_tc.cu — tcgen05 / TMA / TMEM implicit-GEMM convolution for sm_100a.
+//
+// The dense contractions of the shipped graphs (reference backend/models/*/inference.pdmodel: `conv2d` 1x1 / KxK stride 1,
+// `matmul_v2` — SURVEY.md Appendix B/F) run here on the 5th-generation tensor cores:
+//   A  = pixel-major fp16 activations, loaded by TMA straight into 128B-swizzled shared memory
+//        (1x1: 2-D tiles [128 pixels x 64 channels]; KxK: 4-D boxes [1 img][8 rows][16 cols][64 ch] shifted per filter
+//        tap — out-of-bounds rows/columns are zero-filled by TMA, which IS the convolution padding);
+//   B  = fp16 K-major weights [cout][tap][cin] (packed once per plan, L2-resident);
+//   D  = fp32 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld -> bias -> act -> affine -> +residual -> act -> fp16 store
+//        into the (possibly concat-aliased) output slice.
+// Persistent CTAs (one per SM) walk the tile list; warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2-5 = epilogue.  These nets are HBM-bound (35-59 FLOP/B): the point of the tensor cores is to get the FMA work
+// out of the way so that the kernel streams activations at memory speed.
+#include "gemm_tc.h"
+
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "plan.h"
+
+namespace vse {
+
+static constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
+static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+static constexpr int kThreads = 192;
+static constexpr int kMaxSmem = 227 * 1024;
+
+struct TcParams {
+    int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
+        stages, tmem_cols;
+    void* out;
+    int out_cs;
+    const float* bias;
+    const float* post_scale;
+    const float* post_shift;
+    const void* res;
+    int res_cs, act, act2;
+    float hs_slope, hs_offset;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must trap (launch error on the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t spins = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(addr, parity)) {
+        if ((++spins & 0x3FFu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// K-major operand tile in 128B-swizzled shared memory: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr & 0x3FFFFu) >> 4);     // start address
+    d |= uint64_t(1) << 16;                     // leading byte offset (unused for swizzled K-major; canonical 1)
+    d |= uint64_t(1024 >> 4) << 32;             // stride byte offset: next 8-row group
+    d |= uint64_t(1) << 46;                     // descriptor version (Blackwell)
+    d |= uint64_t(2) << 61;                     // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tc_act(float x, int act, float slope, float offset) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(x, 0.f);
+        case ACT_HSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) / 6.f;
+        case ACT_HSIGMOID: return fminf(fmaxf(x * slope + offset, 0.f), 1.f);
+        case ACT_SWISH: return x / (1.f + __expf(-x));
+        case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+        case ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
+        default: return x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = A_BYTES + p.n_chunk * 128;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tmem_full = empty + p.stages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, uint32_t(p.tmem_cols));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.num_m_tiles * p.n_chunks;
+    const int taps = p.kh * p.kw;
+    const int k_iters = taps * p.num_kb;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
+                int img = 0, y0 = 0, x0 = 0;
+                if (p.spatial) {
+                    const int per_img = p.tiles_x * p.tiles_y;
+                    img = m_tile / per_img;
+                    const int r = m_tile - img * per_img;
+                    y0 = (r / p.tiles_x) * 8;
+                    x0 = (r % p.tiles_x) * 16;
+                }
+                for (int it = 0; it < k_iters; it++) {
+                    const int tap = it / p.num_kb, kb = it - tap * p.num_kb;
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], uint32_t(stage_bytes));
+                    uint8_t* a_dst = smem + size_t(stage) * stage_bytes;
+                    if (p.spatial) {
+                        const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                        tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 + kx - p.pw, y0 + ky - p.ph, img);
+                    } else {
+                        tma_load_2d(a_dst, &map_a, &full[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+                    }
+                    tma_load_2d(a_dst + A_BYTES, &map_b, &full[stage], tap * p.k_pad + kb * BLOCK_K, n_idx * p.n_chunk);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            const uint32_t idesc = (1u << 4) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * p.n_chunk);
+                for (int it = 0; it < k_iters; it++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + size_t(stage) * stage_bytes);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                        umma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
+                                 (it | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);   // smem slot is free once these MMAs have read it
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full[acc]);     // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
+            long long pix = -1;
+            if (p.spatial) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                const int img = m_tile / per_img;
+                const int r = m_tile - img * per_img;
+                const int y = (r / p.tiles_x) * 8 + (row >> 4), x = (r % p.tiles_x) * 16 + (row & 15);
+                if (y < p.H && x < p.W) pix = (long long)img * p.H * p.W + (long long)y * p.W + x;
+            } else {
+                const long long m = (long long)m_tile * BLOCK_M + row;
+                if (m < p.M) pix = m;
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
+            const int ch0 = n_idx * p.n_chunk;
+            for (int c0 = 0; c0 < p.n_chunk; c0 += 16) {
+                if (ch0 + c0 >= p.n_store) break;   // warp-uniform
+                uint32_t raw[16];
+                tmem_ld16(taddr + uint32_t(c0), raw);     // .sync.aligned: executed by the whole (converged) warp
+                if (pix >= 0) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int ch = ch0 + c0 + j;
+                        float x = __uint_as_float(raw[j]);
+                        if (ch < p.n_store) {
+                            x += p.bias[ch];
+                            x = tc_act(x, p.act, p.hs_slope, p.hs_offset);
+                            if (p.post_scale) x = x * p.post_scale[ch] + p.post_shift[ch];
+                        }
+                        v[j] = x;
+                    }
+                    __half* o = static_cast<__half*>(p.out) + size_t(pix) * p.out_cs + ch0 + c0;
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; h8++) {
+                        if (ch0 + c0 + h8 * 8 >= p.n_store) break;
+                        if (p.res) {
+                            const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + size_t(pix) * p.res_cs + ch0 + c0 + h8 * 8);
+                            const __half2* rh = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float2 f = __half22float2(rh[j]);
+                                v[h8 * 8 + 2 * j] += f.x;
+                                v[h8 * 8 + 2 * j + 1] += f.y;
+                            }
+                        }
+                        uint4 u;
+                        __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            hh[j] = __floats2half2_rn(tc_act(v[h8 * 8 + 2 * j], p.act2, 0.f, 0.f), tc_act(v[h8 * 8 + 2 * j + 1], p.act2, 0.f, 0.f));
+                        *reinterpret_cast<uint4*>(o + h8 * 8) = u;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+
+TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps) {
+    TcWeights t;
+    const int n_mma = round_up_i(cout, 16);
+    t.n_chunks = (n_mma + 255) / 256;
+    t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, 16);
+    t.k_pad = round_up_i(cin, BLOCK_K);
+    t.taps = taps;
+    const size_t rows = size_t(t.n_chunks) * t.n_chunk, cols = size_t(taps) * t.k_pad;
+    t.b.assign(rows * cols, 0);
+    for (int co = 0; co < cout; co++)
+        for (int tp = 0; tp < taps; tp++)
+            for (int ci = 0; ci < cin; ci++) {
+                __half h = __float2half_rn(w[(size_t(co) * taps + tp) * cin + ci]);
+                uint16_t bits;
+                std::memcpy(&bits, &h, 2);
+                t.b[size_t(co) * cols + size_t(tp) * t.k_pad + ci] = bits;
+            }
+    return t;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                          const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return "cuTensorMapEncodeTiled unavailable";
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), base, dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")";
+    return "";
+}
+
+std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
+                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw) {
+    t.valid = false;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (in_cs & 7)) return "activation view not 16-byte aligned";
+    if (pixels <= 0) return "empty";
+    t.kh = kh; t.kw = kw; t.ph = ph; t.pw = pw;
+    t.k_pad = w.k_pad;
+    t.num_kb = (cin + BLOCK_K - 1) / BLOCK_K;
+    t.n_chunk = w.n_chunk;
+    t.n_chunks = w.n_chunks;
+    std::string err;
+    if (flat) {
+        t.spatial = 0;
+        t.M = int(pixels);
+        t.num_m_tiles = int((pixels + BLOCK_M - 1) / BLOCK_M);
+        cuuint64_t dims[2] = {cuuint64_t(cin), cuuint64_t(pixels)};
+        cuuint64_t strides[1] = {cuuint64_t(in_cs) * 2};
+        cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
+        err = encode(&t.map_a, const_cast<void*>(in), 2, dims, strides, box);
+    } else {
+        t.spatial = 1;
+        t.n_img = n_img; t.H = H; t.W = W;
+        t.tiles_x = (W + 15) / 16;
+        t.tiles_y = (H + 7) / 8;
+        t.num_m_tiles = n_img * t.tiles_x * t.tiles_y;
+        cuuint64_t dims[4] = {cuuint64_t(cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(n_img)};
+        cuuint64_t strides[3] = {cuuint64_t(in_cs) * 2, cuuint64_t(W) * in_cs * 2, cuuint64_t(H) * W * in_cs * 2};
+        cuuint32_t box[4] = {BLOCK_K, 16, 8, 1};
+        err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box);
+    }
+    if (!err.empty()) return err;
+    {
+        cuuint64_t dims[2] = {cuuint64_t(w.taps) * w.k_pad, cuuint64_t(w.n_chunks) * w.n_chunk};
+        cuuint64_t strides[1] = {cuuint64_t(w.taps) * w.k_pad * 2};
+        cuuint32_t box[2] = {BLOCK_K, cuuint32_t(w.n_chunk)};
+        err = encode(&t.map_b, const_cast<void*>(wdev), 2, dims, strides, box);
+        if (!err.empty()) return err;
+    }
+    t.valid = true;
+    return "";
+}
+
+void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
+    TcParams p{};
+    p.spatial = t.spatial; p.M = t.M; p.n_img = t.n_img; p.H = t.H; p.W = t.W; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
+    p.kh = t.kh; p.kw = t.kw; p.ph = t.ph; p.pw = t.pw; p.num_kb = t.num_kb; p.k_pad = t.k_pad;
+    p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = t.num_m_tiles;
+    const int stage_bytes = A_BYTES + t.n_chunk * 128;
+    const int budget = kMaxSmem - 2048;
+    p.stages = std::max(2, std::min(8, budget / stage_bytes));
+    int cols = 32;
+    while (cols < 2 * t.n_chunk) cols *= 2;
+    p.tmem_cols = cols;
+    p.out = t.out; p.out_cs = t.out_cs;
+    p.bias = t.epi.bias; p.post_scale = t.epi.post_scale; p.post_shift = t.epi.post_shift;
+    p.res = t.epi.res; p.res_cs = t.epi.res_cs; p.act = t.epi.act; p.act2 = t.epi.act2;
+    p.hs_slope = t.epi.hs_slope; p.hs_offset = t.epi.hs_offset;
+    const size_t smem = size_t(p.stages) * stage_bytes + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        configured = true;
+    }
+    const int total = t.num_m_tiles * t.n_chunks;
+    const int grid = std::max(1, std::min(total, sm_count));
+    conv_tc_kernel<<<grid, kThreads, smem, st>>>(t.map_a, t.map_b, p);
+}
+
+}  // namespace vse

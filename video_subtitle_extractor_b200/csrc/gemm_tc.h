@@ -1,0 +1,50 @@
+// gemm_tc.h — tcgen05 / TMA implicit-GEMM convolution (sm_100a): launch interface.
+// See gemm_tc.cu for the kernel. One TcConv describes one CONV step on one batch geometry.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "nn_kernels.h"
+
+namespace vse {
+
+struct TcWeights {          // built once per plan step (host), uploaded as fp16
+    int n_chunk = 0;        // accumulator columns per tile (multiple of 16, <= 256)
+    int n_chunks = 0;       // output-channel chunks (tiles along N)
+    int k_pad = 0;          // per-tap K extent in the B matrix (multiple of 64)
+    int taps = 1;
+    std::vector<uint16_t> b;  // fp16 bits, [n_chunks * n_chunk][taps * k_pad], K-major, zero padded
+};
+
+// cout / cin: real channel counts; weights fp32 [cout][kh*kw][cin]
+TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps);
+
+struct TcConv {
+    CUtensorMap map_a;      // activations (2-D flat for 1x1, 4-D [C][W][H][N] for KxK)
+    CUtensorMap map_b;      // weights
+    int spatial = 0;        // 0: 1x1 over a flat pixel list; 1: KxK stride 1 over equal-sized images
+    int M = 0;              // flat: number of pixels
+    int n_img = 0, H = 0, W = 0, tiles_x = 0, tiles_y = 0;
+    int kh = 1, kw = 1, ph = 0, pw = 0;
+    int num_kb = 1;         // 64-channel K blocks per tap
+    int k_pad = 64;
+    int n_chunk = 16, n_chunks = 1, n_store = 8;
+    int num_m_tiles = 0;
+    void* out = nullptr;
+    int out_cs = 0;
+    Epilogue epi;
+    bool valid = false;
+};
+
+// Fills map_a/map_b + tile counts. `in`: activation base (fp16, channel stride in_cs), `wdev`: packed weights on device.
+// Returns an empty string on success, else the reason the step cannot use the tensor-core path.
+std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
+                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw);
+
+void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st);
+
+}  // namespace vse

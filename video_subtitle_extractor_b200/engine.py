@@ -18,6 +18,7 @@ _lib = None
 PLAN_DET, PLAN_REC = 0, 1
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
 PRECISION_FP16, PRECISION_FP32 = 0, 1
+FLAG_NO_TENSOR_CORES = 1
 
 
 class VseConfig(C.Structure):
@@ -35,7 +36,7 @@ class VseResult(C.Structure):
 
 
 EXPORTS = ["vse_default_config", "vse_abi_version", "vse_device_count", "vse_create", "vse_destroy", "vse_last_error",
-           "vse_load_plan", "vse_run", "vse_det_only", "vse_launch_count", "vse_debug_run_plan", "vse_debug_get_value",
+           "vse_load_plan", "vse_run", "vse_det_only", "vse_launch_count", "vse_tc_launch_count", "vse_debug_run_plan", "vse_debug_get_value",
            "vse_debug_resize_bilinear", "vse_debug_db_postprocess", "vse_debug_crop", "vse_debug_time_steps"]
 
 
@@ -66,6 +67,8 @@ def load_library(path: Optional[str] = None):
         fn.argtypes = [vp, pp_u8, p_i32, p_i32, p_i32, i32, i32, C.POINTER(VseResult)]
     lib.vse_launch_count.argtypes = [vp]
     lib.vse_launch_count.restype = i64
+    lib.vse_tc_launch_count.argtypes = [vp]
+    lib.vse_tc_launch_count.restype = i64
     lib.vse_debug_run_plan.argtypes = [vp, i32, pp_u8, i32, i32, p_i32, p_i32, i32]
     lib.vse_debug_get_value.argtypes = [vp, i32, i32, p_f32, i64, p_i32]
     lib.vse_debug_get_value.restype = i64
@@ -100,7 +103,7 @@ class Engine:
     def __init__(self, device: int = 0, precision: int = PRECISION_FP16, rec_image_h: int = 48, rec_image_w: int = 320,
                  rec_batch_num: int = 6, det_limit_side_len: int = 960, det_thresh: float = 0.3,
                  det_box_thresh: float = 0.6, det_unclip_ratio: float = 1.5, max_boxes_per_frame: int = 64,
-                 max_text_len: int = 256):
+                 max_text_len: int = 256, flags: int = 0):
         self.lib = load_library()
         cfg = VseConfig()
         self.lib.vse_default_config(C.byref(cfg))
@@ -109,6 +112,7 @@ class Engine:
         cfg.det_limit_side_len, cfg.det_thresh = det_limit_side_len, det_thresh
         cfg.det_box_thresh, cfg.det_unclip_ratio = det_box_thresh, det_unclip_ratio
         cfg.max_boxes_per_frame = max_boxes_per_frame
+        cfg.flags = flags
         self.cfg = cfg
         self.max_text_len = max_text_len
         self._h = C.c_void_p()
@@ -136,6 +140,10 @@ class Engine:
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
         self._check(self.lib.vse_load_plan(self._h, which, C.cast(buf, C.c_void_p), len(blob)), "vse_load_plan")
         self.plan_names[which] = name
+
+    @property
+    def tc_launch_count(self) -> int:
+        return int(self.lib.vse_tc_launch_count(self._h))
 
     @property
     def launch_count(self) -> int:
