@@ -105,7 +105,7 @@ def test_component_hull_and_min_area_rect_match_cv2(lib):
             exact = False
             if m > 2:
                 ref5 = np.array([r[0][0], r[0][1], r[1][0], r[1][1]], np.float32)
-                exact = np.array_equal(ref5, rect5[:4]) and abs(rect5[4] - np.float32(r[2])) <= 4e-6 * max(1.0, abs(r[2]))
+                exact = np.array_equal(ref5, rect5[:4]) and rect5[4] == np.float32(r[2])
                 bad_rect += not exact
             exact = m > 2 and exact
             rbox, rss = hl.get_mini_boxes(c)
@@ -117,8 +117,37 @@ def test_component_hull_and_min_area_rect_match_cv2(lib):
                 assert np.float32(rss) == np.float32(ss)
     assert tot > 1000
     assert bad_hull <= 0.01 * tot          # only contours that revisit pixels start the hull elsewhere
-    assert bad_rect <= 0.005 * tot         # centre/size bit-exact
-    assert worst < 2e-4                    # corners: 1-ulp angle differences only
+    assert bad_rect == 0                   # centre/size/angle bit-exact
+    assert worst == 0 and bad_box == 0     # and so are the get_mini_boxes corners
+
+
+def test_min_area_rect_rotated_shapes_bit_exact(lib):
+    """Rotated text boxes: cv2.minAreaRect / boxPoints bit for bit (the score mask truncates these corners to ints, so
+    a 1-ulp difference can move a mask edge by a pixel)."""
+    rng = np.random.default_rng(3)
+    tot = 0
+    for _ in range(3000):
+        cx, cy = rng.uniform(50, 900), rng.uniform(50, 500)
+        w, h, ang = rng.uniform(5, 400), rng.uniform(3, 60), rng.uniform(-90, 90)
+        bp = cv2.boxPoints(((cx, cy), (w, h), ang)).astype(np.int32)
+        m = np.zeros((600, 1000), np.uint8)
+        cv2.fillPoly(m, [bp], 1)
+        cs, _ = cv2.findContours(m, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+        if not cs:
+            continue
+        c = cs[0]
+        hull = np.ascontiguousarray(cv2.convexHull(c, clockwise=False, returnPoints=True).reshape(-1, 2).astype(np.int32))
+        if len(hull) < 3:
+            continue
+        r = cv2.minAreaRect(c)
+        box8, rect5 = np.zeros(8, np.float32), np.zeros(5, np.float32)
+        lib.gh_mini_box_from_hull(ip(hull), len(hull), fp(box8), fp(rect5))
+        ref5 = np.array([r[0][0], r[0][1], r[1][0], r[1][1], r[2]], np.float32)
+        assert np.array_equal(ref5, rect5), (hull.tolist(), ref5, rect5)
+        rbox, _ = hl.get_mini_boxes(c)
+        assert np.array_equal(np.array(rbox, np.float32).ravel(), box8)
+        tot += 1
+    assert tot > 2500
 
 
 def _fill_rows(lib, box, W, H):

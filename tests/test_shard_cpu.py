@@ -32,7 +32,8 @@ WORKER = textwrap.dedent("""
     local = [(f, "rank%%d:frame%%d" %% (rank, f)) for f in range(lo, hi)]
     merged = shard.gather_by_frame(local)
     mx = shard.max_over_ranks(float(rank + 1))
-    print("RESULT", rank, hashlib.sha1(got[0]).hexdigest(), got[1].decode(), [m[0] for m in merged], mx, flush=True)
+    line = "RESULT %%d %%s %%s %%s %%s" %% (rank, hashlib.sha1(got[0]).hexdigest(), got[1].decode(), [m[0] for m in merged], mx)
+    open(os.path.join(os.environ["VSE_TEST_OUT"], "rank%%d.txt" %% rank), "w").write(line)   # one file per rank: stdout of two ranks interleaves
     dist.destroy_process_group()
 """) % ROOT
 
@@ -42,10 +43,10 @@ def test_two_gloo_ranks_broadcast_and_merge(tmp_path):
     script.write_text(WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", str(script)]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", VSE_TEST_OUT=str(tmp_path))
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
-    lines = sorted(l for l in r.stdout.splitlines() if l.startswith("RESULT"))
+    lines = sorted(p.read_text() for p in tmp_path.glob("rank*.txt"))
     assert len(lines) == 2
     a, b = (l.split(" ", 3) for l in lines)
     assert a[2] == b[2]                                   # same plan bytes on both ranks

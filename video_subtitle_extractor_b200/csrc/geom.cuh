@@ -270,20 +270,18 @@ VSE_HD inline void rotating_calipers_minarea(const P2f* points, int n, float* wo
     seq[2] = top;
     seq[3] = left;
     for (int k = 0; k < n; k++) {
-        float dp[4] = {
-            +base_a * vect[seq[0]].x + base_b * vect[seq[0]].y,
-            -base_b * vect[seq[1]].x + base_a * vect[seq[1]].y,
-            -base_a * vect[seq[2]].x - base_b * vect[seq[2]].y,
-            +base_b * vect[seq[3]].x - base_a * vect[seq[3]].y,
-        };
-        float maxcos = dp[0] * inv_vect_length[seq[0]];
+        // OpenCV >= 4.5.2 (rotcalipers.cpp): the caliper side with the smallest angle to its polygon edge is found by
+        // cross-product sign tests between the edge vectors rotated into the frame of side 0, not by comparing cosines
+        P2f rv[4];
+        rv[0] = vect[seq[0]];
+        rv[1].x = vect[seq[1]].y;  rv[1].y = -vect[seq[1]].x;   // rotate90CW
+        rv[2].x = -vect[seq[2]].x; rv[2].y = -vect[seq[2]].y;   // rotate180
+        rv[3].x = -vect[seq[3]].y; rv[3].y = vect[seq[3]].x;    // rotate90CCW
         int main_element = 0;
         for (int i = 1; i < 4; ++i) {
-            float cosalpha = dp[i] * inv_vect_length[seq[i]];
-            if (cosalpha > maxcos) {
-                main_element = i;
-                maxcos = cosalpha;
-            }
+            // firstVecIsRight(rv[i], rv[main_element]): rotate90CW(rv[i]) . rv[main] < 0
+            float tx = rv[i].y, ty = -rv[i].x;
+            if (tx * rv[main_element].x + ty * rv[main_element].y < 0) main_element = i;
         }
         {
             int pindex = seq[main_element];
@@ -345,18 +343,20 @@ VSE_HD inline RotRect cv_min_area_rect(const P2f* hpoints, int n, float* work) {
         box.cx = out[0] + (out[2] + out[4]) * 0.5f;
         box.cy = out[1] + (out[3] + out[5]) * 0.5f;
         // OpenCV >= 4.5.1 reports the side whose direction lies in [-90, 0) degrees as "width": while the first side
-        // vector points into [0, 180], step to the next side (a, b) -> (-b, a).  Checked against cv2 4.13: centre and
-        // size bit-exact; the angle is within 1 ulp (tests/test_geom_cpu.py).
+        // vector points into [0, 180], step to the next side (a, b) -> (-b, a) and take 90 degrees off the angle, which
+        // is kept in double until the final cast.  Checked against cv2 4.13 on axis-aligned and rotated shapes: centre,
+        // size and angle bit-exact (tests/test_geom_cpu.py).
         float ax = out[2], ay = out[3], bx = out[4], by = out[5];
-        float ang = (float)atan2((double)ay, (double)ax);
-        for (int it = 0; it < 4 && ang >= 0.f; it++) {
+        double deg = atan2((double)ay, (double)ax) * 180 / VSE_PI;
+        for (int it = 0; it < 4 && deg >= 0; it++) {
             float tx = ax, ty = ay;
             ax = -bx; ay = -by; bx = tx; by = ty;
-            ang = (float)atan2((double)ay, (double)ax);
+            deg -= 90;
         }
         box.w = (float)sqrt((double)ax * ax + (double)ay * ay);
         box.h = (float)sqrt((double)bx * bx + (double)by * by);
-        box.angle = ang;
+        box.angle = (float)deg;
+        return box;
     } else if (n == 2) {
         box.cx = (hpoints[0].x + hpoints[1].x) * 0.5f;
         box.cy = (hpoints[0].y + hpoints[1].y) * 0.5f;
