@@ -158,29 +158,55 @@ def run_reference(args, rank, world):
 def step_roofline(eng, E):
     """Per-kernel achieved HBM GB/s of the dominant kernel, from CUDA events between plan steps (engine stream)."""
     from video_subtitle_extractor_b200 import plan as P
-    rows = []
+    rows, rows_out = [], []
     for which in (E.PLAN_DET, E.PLAN_REC):
         try:
             ms, info = eng.debug_time_steps(which, reps=5)
         except RuntimeError:
             continue
         for t, i in zip(ms, info):
-            op, pin, pout, cin, cout, taps, eb_in, eb_out = (int(v) for v in i)
+            opk, pin, pout, cin, cout, taps, eb_in, eb_out = (int(v) for v in i)
+            op, kind = opk & 0xFF, opk >> 8
+            if kind == 3:          # ran inside the previous step's fused kernel: fold its output bytes into that row
+                w_, n_, t_, b_, f_ = rows[-1]
+                prev_out = rows_out.pop()
+                rows[-1] = (w_, n_, t_ + float(t), b_ - prev_out + pout * eb_out + taps * cin * cout * 4, f_ + 2 * pout * cin * cout)
+                rows_out.append(pout * eb_out)
+                continue
             pad8 = lambda c: (c + 7) // 8 * 8
-            wbytes = taps * cin * cout * 4 if op in (P.OP_CONV, P.OP_STEM) else taps * cin * 4
+            wbytes = taps * cin * cout * 4 if op in (P.OP_CONV, P.OP_STEM, P.OP_DECONV2) else taps * cin * 4
+            if kind == 1:
+                wbytes //= 2       # fp16 weight matrix
+            out_bytes = pout * (cout if eb_out == 4 else pad8(cout)) * eb_out
             if op == P.OP_STEM:
                 bytes_ = pin * 4 + pout * pad8(cout) * eb_out + wbytes
             elif op in (P.OP_CONV, P.OP_DWCONV, P.OP_DECONV2):
-                bytes_ = pin * pad8(cin) * eb_in + pout * (cout if eb_out == 4 else pad8(cout)) * eb_out + wbytes
+                bytes_ = pin * pad8(cin) * eb_in + out_bytes + wbytes
             else:
                 bytes_ = pin * pad8(cin) * eb_in + pout * pad8(cout) * eb_out
-            flops = 2 * pout * cin * cout * taps if op in (P.OP_CONV, P.OP_STEM, P.OP_DECONV2) else 0
-            rows.append((which, P.OP_NAMES[op], float(t), bytes_, flops))
+            flops = 2 * pout * cin * cout * taps if op in (P.OP_CONV, P.OP_STEM) else (2 * pout * cin * cout if op == P.OP_DECONV2 else 0)
+            name = P.OP_NAMES[op]
+            if op == P.OP_CONV:
+                kname = "conv_tc_kernel" if kind == 1 else "conv_simt_kernel"
+            elif op == P.OP_STEM:
+                kname = "stem_fast_kernel" if kind == 2 else "conv_simt_kernel"
+            elif op == P.OP_DWCONV:
+                kname = "dwconv_fast_kernel" if kind == 2 else "dwconv_kernel"
+            elif op == P.OP_DECONV2:
+                kname = "db_head_fused_kernel" if kind == 2 else "deconv2_kernel"
+            else:
+                kname = name.lower() + "_kernel"
+            rows.append((which, kname, float(t), bytes_, flops))
+            rows_out.append(out_bytes if op in (P.OP_CONV, P.OP_DWCONV, P.OP_DECONV2) else 0)
     if not rows:
         return None, []
+    if os.environ.get("VSE_STEP_TABLE"):       # per-step dump for profiling notes (profiles/)
+        with open(os.environ["VSE_STEP_TABLE"], "w") as f:
+            f.write("plan kernel ms bytes GB/s GFLOP\n")
+            for which, k, t, b, fl in rows:
+                f.write(f"{which} {k} {t:.4f} {b} {b / max(t, 1e-6) / 1e6:.1f} {fl / 1e9:.3f}\n")
     by_kernel = {}
-    for which, name, t, b, f in rows:
-        k = "conv_simt_kernel" if name in ("CONV", "STEM") else name.lower() + "_kernel"
+    for which, k, t, b, f in rows:
         a = by_kernel.setdefault(k, [0.0, 0, 0, 0])
         a[0] += t; a[1] += b; a[2] += f; a[3] += 1
     top = max(by_kernel.items(), key=lambda kv: kv[1][0])
@@ -307,7 +333,8 @@ def run_b200(args, rank, local_rank, world):
                         "peak_source": peak_src, "launches_per_step": n_launch,
                         "algorithmic_bytes_per_launch": bytes_ / n_launch, "avg_launch_ms": t_ms / n_launch,
                         "tflops": flops / (t_ms * 1e-3) / 1e12,
-                        "per_kernel_ms": {k: round(t, 4) for k, t, _, _, _ in table}}
+                        "per_kernel_ms": {k: round(t, 4) for k, t, _, _, _ in table},
+                        "per_kernel_gbs": {k: round(b / max(t, 1e-6) / 1e6, 1) for k, t, b, _, _ in table}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             oracle, cores = cpu_oracle(det_blob, rec_blob)

@@ -45,7 +45,10 @@ typedef enum {
 enum { VSE_MEM_HOST = 0, VSE_MEM_PINNED = 1, VSE_MEM_DEVICE = 2 };
 enum { VSE_PLAN_DET = 0, VSE_PLAN_REC = 1 };
 enum { VSE_PRECISION_FP16 = 0, VSE_PRECISION_FP32 = 1 };
-enum { VSE_FLAG_NO_TENSOR_CORES = 1 };  /* vse_config.flags: keep every conv on the CUDA-core kernels (A/B checks) */
+enum {
+    VSE_FLAG_NO_TENSOR_CORES = 1, /* vse_config.flags: keep every conv on the CUDA-core kernels (A/B checks)      */
+    VSE_FLAG_NO_FAST_KERNELS = 2  /* keep depthwise / stem / DB-head steps on the generic kernels (A/B checks)     */
+};
 
 /* Mirrors the knobs the reference passes to PaddleOCR / TextDetector (ocr.py:91-113) and the
  * upstream defaults it relies on (utility.parse_args(): SURVEY.md Appendix D.8 item 3). */
@@ -124,7 +127,7 @@ int  vse_debug_crop(vse_engine* e, const uint8_t* frame, int32_t h, int32_t w, c
                     uint8_t* out_bgr, int32_t capacity, int32_t* out_h, int32_t* out_w);
 
 /* Re-runs the steps of the last run of plan `which` with a CUDA event between steps (on the engine's stream);
- * ms[k] = mean device time of step k; info[k][8] = {op, in_pixels, out_pixels, cin, cout, taps, in_elt_bytes,
+ * ms[k] = mean device time of step k; info[k][8] = {op | kernel_kind << 8 (0 generic, 1 tcgen05, 2 specialised, 3 fused into the previous step), in_pixels, out_pixels, cin, cout, taps, in_elt_bytes,
  * out_elt_bytes}.  Returns the number of steps.  bench.py derives the per-kernel roofline from this. */
 int  vse_debug_time_steps(vse_engine* e, int32_t which, int32_t reps, float* ms, int64_t* info, int32_t capacity);
 

@@ -2,6 +2,7 @@
 // Replaces the paddle.inference predictor runs behind reference backend/tools/ocr.py:27 and
 // backend/tools/subtitle_detect.py:25 (see include/vse_b200.h for the boundary).
 #include "engine.h"
+#include "fast_kernels.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -91,10 +92,13 @@ void Engine::prepare_plan(LoadedPlan& lp) {
                     for (int t = 0; t < kh * kw; t++)
                         for (int ci = 0; ci < cin; ci++)
                             host[o.w + (size_t(t) * d.w_ci + ci) * d.w_co + co] = src[(size_t(co) * kh * kw + t) * cin + ci];
-                o.bias = put_vec(pd.w(s, W_BIAS), cout, d.w_co);
+                // zero padded past the tensor-core tile grid (n_chunks * n_chunk <= cout + 16 * n_chunks): the epilogue reads
+                // these per 4 channels without bounds checks
+                const int vec_pad = d.w_co + 512;
+                o.bias = put_vec(pd.w(s, W_BIAS), cout, vec_pad);
                 if (s.p[P_HAS_POST]) {
-                    o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, d.w_co);
-                    o.pb = put_vec(pd.w(s, W_POST_SHIFT), cout, d.w_co);
+                    o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, vec_pad);
+                    o.pb = put_vec(pd.w(s, W_POST_SHIFT), cout, vec_pad);
                 }
                 break;
             }
@@ -495,6 +499,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
         }
     };
     if (step_events) cudaEventRecord((*step_events)[0], stream);
+    cx.kind.assign(pd.steps.size(), 0);   // 0 generic kernel, 1 tcgen05 GEMM, 2 specialised kernel, 3 fused into the previous step
     for (size_t k = 0; k < pd.steps.size(); k++) {
         if (step_events && k > 0) cudaEventRecord((*step_events)[k], stream);
         const StepRec& s = pd.steps[k];
@@ -522,14 +527,46 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 a.kh = s.p[P_KH]; a.kw = s.p[P_KW]; a.sh = s.p[P_SH]; a.sw = s.p[P_SW]; a.ph = s.p[P_PH]; a.pw = s.p[P_PW];
                 a.out_f32 = out_f32;
                 for (int i = 0; i < 3; i++) { a.nscale[i] = pd.hdr.norm_scale[i]; a.nshift[i] = pd.hdr.norm_shift[i]; }
+                const bool fast = prec == 0 && !(cfg.flags & VSE_FLAG_NO_FAST_KERNELS);
+                auto max_units = [&](int tw) {   // max over images of out_h * ceil(out_w / tw)
+                    int m = 0;
+                    for (const ImgTab& t : geo_of(s.out).tab) m = std::max(m, t.h * ((t.w + tw - 1) / tw));
+                    return m;
+                };
                 if (s.op == OP_DWCONV) {
                     if (out_f32) throw InvalidArg{"depthwise conv cannot produce a fetched output"};
-                    launch_dwconv(a, prec, stream);
+                    if (fast && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
+                    else launch_dwconv(a, prec, stream);
                 } else if (s.op == OP_DECONV2) {
-                    launch_deconv2(a, s.p[P_COUT], prec, stream);
+                    // DB head: deconv(C->C)+ReLU feeding only a deconv(C->1)+sigmoid that is a fetched fp32 map -> one kernel
+                    bool fused = false;
+                    if (fast && !last_keep_all_[which] && k + 1 < pd.steps.size()) {
+                        const StepRec& s2 = pd.steps[k + 1];
+                        const ValueRec& v2 = pd.values[s2.out];
+                        if (s2.op == OP_DECONV2 && s2.ins[0] == s.out && pd.values[s.out].last_use == int(k + 1) &&
+                            pd.values[s.out].alias_of < 0 && s.p[P_CIN] == s.p[P_COUT] && s2.p[P_CIN] == s.p[P_COUT] &&
+                            s2.p[P_COUT] == 1 && v2.dtype == DT_F32 && v2.kind == KIND_IMG && s.p[P_ACT] == ACT_RELU &&
+                            s2.p[P_ACT] == ACT_SIGMOID && !s.p[P_HAS_POST] && !s2.p[P_HAS_POST] && !s.p[P_HAS_RES] &&
+                            !s2.p[P_HAS_RES] && s.p[P_ACT2] == ACT_NONE && s2.p[P_ACT2] == ACT_NONE) {
+                            const StepDev& d2 = lp.dev[k + 1];
+                            fused = launch_db_head_fused(a.in, a.in_cs, s.p[P_CIN], d.w, d.bias, d2.w, d2.bias,
+                                                         static_cast<float*>(ptr_of(s2.out)), value_cs(pd, s2.out), a.tin,
+                                                         tab_of(s2.out), cx.n_img, geo_of(s.ins[0]).max_pix, stream);
+                        }
+                    }
+                    if (fused) {
+                        cx.kind[k] = 2;
+                        k++;   // the second transposed convolution ran inside the fused kernel
+                        cx.kind[k] = 3;
+                        if (step_events) cudaEventRecord((*step_events)[k], stream);
+                    } else {
+                        launch_deconv2(a, s.p[P_COUT], prec, stream);
+                    }
+                } else if (s.op == OP_STEM && fast && launch_stem_fast(a, s.p[P_COUT], max_units(2), stream)) {
+                    cx.kind[k] = 2;
                 } else {
                     if (out_f32) a.cout_store = s.p[P_COUT];
-                    launch_conv(which, int(k), a, prec);
+                    if (launch_conv(which, int(k), a, prec)) cx.kind[k] = 1;
                 }
                 launches++;
                 break;
@@ -663,7 +700,7 @@ int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
             return g >= 0 ? cx.geos[g].total : 0;
         };
         int64_t* o = info + size_t(k) * 8;
-        o[0] = s.op;
+        o[0] = s.op | (int64_t(k < int(cx.kind.size()) ? cx.kind[k] : 0) << 8);
         o[1] = pixels(s.ins[0]);
         o[2] = pixels(s.out);
         o[3] = s.ins[0] >= 0 ? pd.values[s.ins[0]].channels : 0;
@@ -675,7 +712,7 @@ int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
     return n;
 }
 
-void Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
+bool Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
     TcConv& t = ctx_[which].tc[step];
     if (prec == 0 && t.valid) {
         t.out = a.out;
@@ -684,9 +721,10 @@ void Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
         t.epi = a.epi;
         launch_conv_tc(t, sm_count, stream);
         tc_launches++;
-        return;
+        return true;
     }
     launch_conv_simt(a, prec, stream);
+    return false;
 }
 
 int64_t Engine::get_value(int which, int vid, float* out, int64_t cap, int32_t* channels) {

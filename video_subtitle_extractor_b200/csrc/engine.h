@@ -125,6 +125,7 @@ struct ExecContext {
     size_t scratch_off = 0, scratch_bytes = 0;
     int n_img = 0;
     std::vector<TcConv> tc;   // per step; valid => the step runs on the tcgen05 kernel for this geometry
+    std::vector<int> kind;    // per step, filled by exec_steps: which kernel family ran (see Engine::time_steps)
 };
 
 class Engine {
@@ -171,7 +172,7 @@ class Engine {
     size_t elt_size(const ValueRec& v) const;
     int value_cs(const PlanData& pd, int vid) const;  // channel stride in elements
     void* vptr(int which, int vid) const;
-    void launch_conv(int which, int step, const ConvArgs& a, int prec);
+    bool launch_conv(int which, int step, const ConvArgs& a, int prec);   // true: ran on the tcgen05 kernel
     const uint8_t* input_ptr_[2] = {nullptr, nullptr};
 
     LoadedPlan plans_[2];

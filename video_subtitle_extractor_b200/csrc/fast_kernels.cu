@@ -1,0 +1,335 @@
+// fast_kernels.cu — shape-specialised fp16 kernels for the HBM-bound steps of the shipped "mobile" graphs
+// (reference backend/models/V4/ch_det_fast, V4/*_rec_fast: PP-LCNetV3 blocks = depthwise KxK + 1x1, DB head = two
+// conv_transpose 2x2 s2).  Same arithmetic as the generic kernels in nn_kernels.cu (fp32
+// accumulate, fp16 storage); what changes is the work per thread:
+//   * depthwise KxK: one thread = a strip of TW output pixels x 8 channels, so every input vector is loaded once per
+//     strip row instead of once per tap, and the filter row lives in registers;
+//   * stem 3x3 s2 (u8 BGRX -> 16 ch): two output pixels per thread, filter bank in shared memory, normalisation fused;
+//   * DB head: conv_transpose(24->24)+ReLU and conv_transpose(24->1)+sigmoid fused — one thread turns one neck pixel
+//     into its 4x4 patch of the probability map; the 272x480x24 intermediate never goes to HBM.
+// The engine falls back to the generic kernels for any other shape.
+#include "fast_kernels.h"
+
+#include <cuda_fp16.h>
+
+#include "plan.h"
+
+namespace vse {
+
+static inline int cdiv_i(int64_t a, int64_t b) { return int((a + b - 1) / b); }
+
+__device__ __forceinline__ void load8h(const __half* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8h(__half* p, const float* v) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <int ACT>
+__device__ __forceinline__ float fact(float x) {
+    if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
+    else if constexpr (ACT == ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    else return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise KxK
+// ------------------------------------------------------------------------------------------------
+struct DwDev {
+    const __half* in; __half* out; const float* w; const float* bias; const float* ps; const float* pt;
+    const ImgTab* tin; const ImgTab* tout;
+    int in_cs, out_cs, cvecs, cp, ph, pw;
+};
+
+template <int K, int SH, int SW, int TW, int ACT>
+__global__ void __launch_bounds__(256) dwconv_fast_kernel(DwDev p) {
+    const int img = blockIdx.y;
+    const ImgTab ti = p.tin[img], to = p.tout[img];
+    const int strips = (to.w + TW - 1) / TW;
+    const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (idx >= int64_t(to.h) * strips * p.cvecs) return;
+    const int cv = int(idx % p.cvecs);
+    const int s = int(idx / p.cvecs);
+    const int oy = s / strips, ox0 = (s - oy * strips) * TW;
+    const int c0 = cv * 8;
+    constexpr int IW = (TW - 1) * SW + K;
+    float acc[TW][8];
+#pragma unroll
+    for (int t = 0; t < TW; t++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[t][j] = 0.f;
+    const int iy0 = oy * SH - p.ph, ix0 = ox0 * SW - p.pw;
+#pragma unroll
+    for (int ky = 0; ky < K; ky++) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= ti.h) continue;
+        float w[K][8];
+#pragma unroll
+        for (int kx = 0; kx < K; kx++) {
+            const float* wp = p.w + size_t(ky * K + kx) * p.cp + c0;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(wp)), b = __ldg(reinterpret_cast<const float4*>(wp + 4));
+            w[kx][0] = a.x; w[kx][1] = a.y; w[kx][2] = a.z; w[kx][3] = a.w;
+            w[kx][4] = b.x; w[kx][5] = b.y; w[kx][6] = b.z; w[kx][7] = b.w;
+        }
+        const __half* rowp = p.in + (size_t(ti.off) + size_t(iy) * ti.w) * p.in_cs + c0;
+#pragma unroll
+        for (int i = 0; i < IW; i++) {
+            const int ix = ix0 + i;
+            if (ix < 0 || ix >= ti.w) continue;
+            float x[8];
+            load8h(rowp + size_t(ix) * p.in_cs, x);
+#pragma unroll
+            for (int t = 0; t < TW; t++) {
+                const int kx = i - t * SW;   // compile-time after unrolling
+                if (kx >= 0 && kx < K) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[t][j] = fmaf(x[j], w[kx][j], acc[t][j]);
+                }
+            }
+        }
+    }
+    float b[8], sc[8], sh[8];
+    {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0)), a1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
+        b[0] = a0.x; b[1] = a0.y; b[2] = a0.z; b[3] = a0.w; b[4] = a1.x; b[5] = a1.y; b[6] = a1.z; b[7] = a1.w;
+    }
+    const bool post = p.ps != nullptr;
+    if (post) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.ps + c0)), s1 = __ldg(reinterpret_cast<const float4*>(p.ps + c0 + 4));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.pt + c0)), t1 = __ldg(reinterpret_cast<const float4*>(p.pt + c0 + 4));
+        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+        sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+    }
+    __half* orow = p.out + (size_t(to.off) + size_t(oy) * to.w) * p.out_cs + c0;
+#pragma unroll
+    for (int t = 0; t < TW; t++) {
+        const int ox = ox0 + t;
+        if (ox >= to.w) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float x = fact<ACT>(acc[t][j] + b[j]);
+            if (post) x = x * sc[j] + sh[j];
+            v[j] = x;
+        }
+        store8h(orow + size_t(ox) * p.out_cs, v);
+    }
+}
+
+template <int K, int SH, int SW>
+static bool dw_launch_act(const DwDev& d, const ConvArgs& a, int max_out_w_strips_pix, cudaStream_t st) {
+    constexpr int TW = 4;
+    // upper bound of threads per image: every image has at most max_out_pix pixels; strips <= ceil(w / TW) per row, so
+    // h * strips <= (pix + h * (TW - 1)) / TW <= pix (for TW >= 1) — use pix / TW + h_max as a safe bound via max_out_pix
+    dim3 grid(cdiv_i(int64_t(max_out_w_strips_pix) * d.cvecs, 256), a.n_img);
+    switch (a.epi.act) {
+        case ACT_NONE: dwconv_fast_kernel<K, SH, SW, TW, ACT_NONE><<<grid, 256, 0, st>>>(d); return true;
+        case ACT_RELU: dwconv_fast_kernel<K, SH, SW, TW, ACT_RELU><<<grid, 256, 0, st>>>(d); return true;
+        case ACT_HSWISH: dwconv_fast_kernel<K, SH, SW, TW, ACT_HSWISH><<<grid, 256, 0, st>>>(d); return true;
+        default: return false;
+    }
+}
+
+bool launch_dwconv_fast(const ConvArgs& a, int max_strip_units, cudaStream_t st) {
+    if (a.epi.res || a.epi.act2 != ACT_NONE || a.out_f32 || a.kh != a.kw) return false;
+    if (2 * a.ph != a.kh - 1 || 2 * a.pw != a.kw - 1) return false;
+    DwDev d{static_cast<const __half*>(a.in), static_cast<__half*>(a.out), a.w, a.epi.bias, a.epi.post_scale, a.epi.post_shift,
+            a.tin, a.tout, a.in_cs, a.out_cs, a.cin_pad / 8, a.cin_pad, a.ph, a.pw};
+    if (!d.bias) return false;
+    const int key = a.kh * 100 + a.sh * 10 + a.sw;
+    switch (key) {
+        case 311: return dw_launch_act<3, 1, 1>(d, a, max_strip_units, st);
+        case 322: return dw_launch_act<3, 2, 2>(d, a, max_strip_units, st);
+        case 321: return dw_launch_act<3, 2, 1>(d, a, max_strip_units, st);
+        case 312: return dw_launch_act<3, 1, 2>(d, a, max_strip_units, st);
+        case 511: return dw_launch_act<5, 1, 1>(d, a, max_strip_units, st);
+        case 522: return dw_launch_act<5, 2, 2>(d, a, max_strip_units, st);
+        case 521: return dw_launch_act<5, 2, 1>(d, a, max_strip_units, st);
+        case 512: return dw_launch_act<5, 1, 2>(d, a, max_strip_units, st);
+        default: return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: 3x3 stride 2 pad 1, uint8 BGRX -> 16 channels, (x * nscale + nshift) fused into the load
+// ------------------------------------------------------------------------------------------------
+struct StemDev {
+    const unsigned char* in; __half* out; const float* w; const float* bias; const ImgTab* tin; const ImgTab* tout;
+    int out_cs, w_ci, w_co, act;
+    float nscale[3], nshift[3];
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
+    __shared__ __align__(16) float sw[27 * 16];   // [(ky*3+kx)*3 + ci][co]
+    __shared__ float sb[16];
+    for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) {
+        const int co = i & 15, r = i >> 4, ci = r % 3, tap = r / 3;
+        sw[i] = p.w[(size_t(tap) * p.w_ci + ci) * p.w_co + co];
+    }
+    if (threadIdx.x < 16) sb[threadIdx.x] = p.bias[threadIdx.x];
+    __syncthreads();
+    const int img = blockIdx.y;
+    const ImgTab ti = p.tin[img], to = p.tout[img];
+    const int pairs = (to.w + 1) >> 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= to.h * pairs) return;
+    const int oy = idx / pairs, ox0 = (idx - oy * pairs) * 2;
+    float acc[2][16];
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[t][j] = sb[j];
+    const int iy0 = oy * 2 - 1, ix0 = ox0 * 2 - 1;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= ti.h) continue;
+        const uchar4* rowp = reinterpret_cast<const uchar4*>(p.in) + size_t(ti.off) + size_t(iy) * ti.w;
+        float px[5][3];
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const int ix = ix0 + i;
+            if (ix >= 0 && ix < ti.w && ix < ti.vw) {
+                const uchar4 u = __ldg(rowp + ix);
+                px[i][0] = float(u.x) * p.nscale[0] + p.nshift[0];
+                px[i][1] = float(u.y) * p.nscale[1] + p.nshift[1];
+                px[i][2] = float(u.z) * p.nscale[2] + p.nshift[2];
+            } else {
+                px[i][0] = px[i][1] = px[i][2] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++) {
+                const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * 16);
+                float w[16];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 f = wp[q];
+                    w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+                }
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const float x = px[kx + 2 * t][ci];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acc[t][j] = fmaf(x, w[j], acc[t][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int ox = ox0 + t;
+        if (ox >= to.w) break;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = fact<ACT>(acc[t][j]);
+        __half* o = p.out + (size_t(to.off) + size_t(oy) * to.w + ox) * p.out_cs;
+        store8h(o, v);
+        store8h(o + 8, v + 8);
+    }
+}
+
+bool launch_stem_fast(const ConvArgs& a, int cout, int max_out_pix_pairs, cudaStream_t st) {
+    if (!a.in_u8 || a.kh != 3 || a.kw != 3 || a.sh != 2 || a.sw != 2 || a.ph != 1 || a.pw != 1 || cout != 16 || a.out_f32) return false;
+    if (a.epi.res || a.epi.post_scale || a.epi.act2 != ACT_NONE || !a.epi.bias || a.out_cs < 16) return false;
+    StemDev d{static_cast<const unsigned char*>(a.in), static_cast<__half*>(a.out), a.w, a.epi.bias, a.tin, a.tout,
+              a.out_cs, a.w_ci, a.w_co, a.epi.act, {a.nscale[0], a.nscale[1], a.nscale[2]}, {a.nshift[0], a.nshift[1], a.nshift[2]}};
+    dim3 grid(cdiv_i(max_out_pix_pairs, 128), a.n_img);
+    switch (a.epi.act) {
+        case ACT_NONE: stem_fast_kernel<ACT_NONE><<<grid, 128, 0, st>>>(d); return true;
+        case ACT_RELU: stem_fast_kernel<ACT_RELU><<<grid, 128, 0, st>>>(d); return true;
+        case ACT_HSWISH: stem_fast_kernel<ACT_HSWISH><<<grid, 128, 0, st>>>(d); return true;
+        default: return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DB head: conv_transpose2x2s2(C->C)+ReLU -> conv_transpose2x2s2(C->1)+sigmoid, fused.  fp32 probability map out.
+// w1: [pos][C][C] (cout-major rows of cin), w2: [pos][8][C] (row 0 is the single output channel)
+// ------------------------------------------------------------------------------------------------
+struct HeadDev {
+    const __half* in; float* out; const float* w1; const float* b1; const float* w2; const float* b2;
+    const ImgTab* tin; const ImgTab* tout;
+    int in_cs;
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) db_head_fused_kernel(HeadDev p) {
+    __shared__ __align__(16) float sw1[4 * C * C];
+    __shared__ __align__(16) float sw2[4 * C];
+    __shared__ float sb1[C];
+    for (int i = threadIdx.x; i < 4 * C * C; i += blockDim.x) sw1[i] = p.w1[i];
+    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sw2[i] = p.w2[size_t(i / C) * 8 * C + (i % C)];
+    if (threadIdx.x < C) sb1[threadIdx.x] = p.b1[threadIdx.x];
+    __syncthreads();
+    const float b2 = p.b2[0];
+    const int img = blockIdx.y;
+    const ImgTab ti = p.tin[img], to = p.tout[img];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ti.h * ti.w) return;
+    const int iy = idx / ti.w, ix = idx - iy * ti.w;
+    float x[C];
+    const __half* ip = p.in + (size_t(ti.off) + idx) * p.in_cs;
+#pragma unroll
+    for (int c = 0; c < C; c += 8) load8h(ip + c, x + c);
+    float o[4][4];   // [row 2*dy1+dy2][col 2*dx1+dx2]
+#pragma unroll
+    for (int pos1 = 0; pos1 < 4; pos1++) {
+        float mid[C];
+#pragma unroll
+        for (int co = 0; co < C; co++) {
+            const float4* wr = reinterpret_cast<const float4*>(sw1 + (pos1 * C + co) * C);
+            float m = sb1[co];
+#pragma unroll
+            for (int q = 0; q < C / 4; q++) {
+                const float4 w = wr[q];
+                m = fmaf(x[4 * q], w.x, m); m = fmaf(x[4 * q + 1], w.y, m);
+                m = fmaf(x[4 * q + 2], w.z, m); m = fmaf(x[4 * q + 3], w.w, m);
+            }
+            mid[co] = fmaxf(m, 0.f);
+        }
+#pragma unroll
+        for (int pos2 = 0; pos2 < 4; pos2++) {
+            const float4* wr = reinterpret_cast<const float4*>(sw2 + pos2 * C);
+            float s = b2;
+#pragma unroll
+            for (int q = 0; q < C / 4; q++) {
+                const float4 w = wr[q];
+                s = fmaf(mid[4 * q], w.x, s); s = fmaf(mid[4 * q + 1], w.y, s);
+                s = fmaf(mid[4 * q + 2], w.z, s); s = fmaf(mid[4 * q + 3], w.w, s);
+            }
+            o[2 * (pos1 >> 1) + (pos2 >> 1)][2 * (pos1 & 1) + (pos2 & 1)] = 1.f / (1.f + __expf(-s));
+        }
+    }
+    float* op = p.out + size_t(to.off) + size_t(4 * iy) * to.w + 4 * ix;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        *reinterpret_cast<float4*>(op + size_t(r) * to.w) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
+}
+
+bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, const float* b1, const float* w2, const float* b2,
+                          float* out, int out_cs, const ImgTab* tin, const ImgTab* tout, int n_img, int max_in_pix,
+                          cudaStream_t st) {
+    if (c != 24 || out_cs != 1 || (in_cs & 7) || !b1 || !b2) return false;
+    if (reinterpret_cast<uintptr_t>(out) & 15) return false;
+    HeadDev d{static_cast<const __half*>(in), out, w1, b1, w2, b2, tin, tout, in_cs};
+    dim3 grid(cdiv_i(max_in_pix, 128), n_img);
+    db_head_fused_kernel<24><<<grid, 128, 0, st>>>(d);
+    return true;
+}
+
+}  // namespace vse

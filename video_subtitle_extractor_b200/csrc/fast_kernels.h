@@ -1,0 +1,22 @@
+// fast_kernels.h — shape-specialised fp16 kernels (see fast_kernels.cu).  Every launcher returns false when the step
+// does not have the shape it was written for; the engine then uses the generic kernel of nn_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "nn_kernels.h"
+
+namespace vse {
+
+// depthwise KxK (K = 3 | 5, strides 1/2 per axis, "same" padding).  max_strip_units = max over images of
+// out_h * ceil(out_w / 4).
+bool launch_dwconv_fast(const ConvArgs& a, int max_strip_units, cudaStream_t st);
+
+// 3x3 stride-2 stem on uint8 BGRX input, 16 output channels.  max_out_pix_pairs = max over images of out_h * ceil(out_w / 2).
+bool launch_stem_fast(const ConvArgs& a, int cout, int max_out_pix_pairs, cudaStream_t st);
+
+// fused DB head (two 2x2 stride-2 transposed convolutions, 24 -> 24 -> 1, ReLU / sigmoid), fp32 map out
+bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, const float* b1, const float* w2, const float* b2,
+                          float* out, int out_cs, const ImgTab* tin, const ImgTab* tout, int n_img, int max_in_pix,
+                          cudaStream_t st);
+
+}  // namespace vse

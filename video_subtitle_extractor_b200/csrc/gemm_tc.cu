@@ -24,7 +24,9 @@ namespace vse {
 
 static constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-static constexpr int kThreads = 192;
+static constexpr int kEpiWarps = 8;
+static constexpr int kThreads = 64 + 32 * kEpiWarps;
+static constexpr int kParamSmemMaxCh = 1024;   // bias/scale/shift of up to this many channels are staged in shared memory
 static constexpr int kMaxSmem = 227 * 1024;
 
 struct TcParams {
@@ -38,6 +40,8 @@ struct TcParams {
     const void* res;
     int res_cs, act, act2;
     float hs_slope, hs_offset;
+    int n_total;       // n_chunks * n_chunk (bias / post arrays are readable up to here)
+    int param_smem;    // 1: bias/scale/shift staged in shared memory
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -141,15 +145,144 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// activation with the kind known at compile time (the epilogue loop is instantiated per activation)
+template <int ACT>
+__device__ __forceinline__ float act_t(float x, float slope, float offset) {
+    if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
+    else if constexpr (ACT == ACT_HSWISH) return x * __saturatef(fmaf(x, 1.f / 6.f, 0.5f));   // x * clip(x + 3, 0, 6) / 6
+    else if constexpr (ACT == ACT_HSIGMOID) return __saturatef(fmaf(x, slope, offset));
+    else if constexpr (ACT == ACT_SWISH) return __fdividef(x, 1.f + __expf(-x));
+    else if constexpr (ACT == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
+    else if constexpr (ACT == ACT_RELU6) return fminf(fmaxf(x, 0.f), 6.f);
+    else return x;
+}
+
 __device__ __forceinline__ float tc_act(float x, int act, float slope, float offset) {
     switch (act) {
         case ACT_RELU: return fmaxf(x, 0.f);
-        case ACT_HSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) / 6.f;
-        case ACT_HSIGMOID: return fminf(fmaxf(x * slope + offset, 0.f), 1.f);
-        case ACT_SWISH: return x / (1.f + __expf(-x));
-        case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+        case ACT_HSWISH: return x * __saturatef(fmaf(x, 1.f / 6.f, 0.5f));
+        case ACT_HSIGMOID: return __saturatef(fmaf(x, slope, offset));
+        case ACT_SWISH: return __fdividef(x, 1.f + __expf(-x));
+        case ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-x));
         case ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
         default: return x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue: 8 warps.  Warp w may only touch TMEM lanes [32 * (w % 4), +32) (hardware rule), so q = w % 4 picks the
+// 32 output pixels (one per lane) and `half` splits the accumulator columns in 32-column pairs between the two warps
+// that share a lane quarter.  Per 16 columns: tcgen05.ld -> +bias -> act -> affine -> (+residual -> act2) -> fp16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int ACT, bool POST>
+__device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* raw, const float* pb, const float* ps,
+                                            const float* pt, int cb, long long pix) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; j4++) {
+        const float4 b = ld4(pb + cb + 4 * j4);
+        float x0 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 0]) + b.x, p.hs_slope, p.hs_offset);
+        float x1 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 1]) + b.y, p.hs_slope, p.hs_offset);
+        float x2 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 2]) + b.z, p.hs_slope, p.hs_offset);
+        float x3 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 3]) + b.w, p.hs_slope, p.hs_offset);
+        if constexpr (POST) {
+            const float4 sc = ld4(ps + cb + 4 * j4), sh = ld4(pt + cb + 4 * j4);
+            x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y); x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
+        }
+        v[4 * j4 + 0] = x0; v[4 * j4 + 1] = x1; v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
+    }
+    if (pix < 0) return;
+    __half* o = static_cast<__half*>(p.out) + size_t(pix) * p.out_cs + cb;
+#pragma unroll
+    for (int h8 = 0; h8 < 2; h8++) {
+        if (cb + h8 * 8 >= p.n_store) break;
+        if (p.res) {
+            const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + size_t(pix) * p.res_cs + cb + h8 * 8);
+            const __half2* rh = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __half22float2(rh[j]);
+                v[h8 * 8 + 2 * j] += f.x;
+                v[h8 * 8 + 2 * j + 1] += f.y;
+            }
+        }
+        if (p.act2 != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[h8 * 8 + j] = tc_act(v[h8 * 8 + j], p.act2, 0.f, 0.f);
+        }
+        uint4 u;
+        __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) hh[j] = __floats2half2_rn(v[h8 * 8 + 2 * j], v[h8 * 8 + 2 * j + 1]);
+        *reinterpret_cast<uint4*>(o + h8 * 8) = u;
+    }
+}
+
+template <int ACT, bool POST>
+__device__ __noinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                           const float* pb, const float* ps, const float* pt, int q, int half, int lane) {
+    const int row = q * 32 + lane;
+    const int total_tiles = p.num_m_tiles * p.n_chunks;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
+        long long pix = -1;
+        if (p.spatial) {
+            const int per_img = p.tiles_x * p.tiles_y;
+            const int img = m_tile / per_img;
+            const int r = m_tile - img * per_img;
+            const int y = (r / p.tiles_x) * 8 + (row >> 4), x = (r % p.tiles_x) * 16 + (row & 15);
+            if (y < p.H && x < p.W) pix = (long long)img * p.H * p.W + (long long)y * p.W + x;
+        } else {
+            const long long m = (long long)m_tile * BLOCK_M + row;
+            if (m < p.M) pix = m;
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
+        const int ch0 = n_idx * p.n_chunk;
+        for (int c0 = half * 32; c0 < p.n_chunk; c0 += 64) {
+            if (ch0 + c0 >= p.n_store) break;   // warp-uniform
+            const bool two = c0 + 16 < p.n_chunk && ch0 + c0 + 16 < p.n_store;
+            uint32_t raw0[16], raw1[16];
+            tmem_ld16_nowait(taddr + uint32_t(c0), raw0);            // .sync.aligned: whole (converged) warp
+            if (two) tmem_ld16_nowait(taddr + uint32_t(c0 + 16), raw1);
+            tmem_ld_wait();
+            epi_chunk16<ACT, POST>(p, raw0, pb, ps, pt, ch0 + c0, pix);
+            if (two) epi_chunk16<ACT, POST>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix);
+            __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+    }
+}
+
+template <bool POST>
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                  const float* pb, const float* ps, const float* pt, int q, int half, int lane) {
+    switch (p.act) {
+        case ACT_RELU: epilogue_loop<ACT_RELU, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
+        case ACT_HSWISH: epilogue_loop<ACT_HSWISH, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
+        case ACT_HSIGMOID: epilogue_loop<ACT_HSIGMOID, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
+        case ACT_SWISH: epilogue_loop<ACT_SWISH, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
+        case ACT_SIGMOID: epilogue_loop<ACT_SIGMOID, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
+        case ACT_RELU6: epilogue_loop<ACT_RELU6, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
+        default: epilogue_loop<ACT_NONE, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
     }
 }
 
@@ -166,6 +299,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tmem_full = empty + p.stages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* sparam = reinterpret_cast<float*>(smem + size_t(p.stages) * stage_bytes + 256);
+    const float *pb = p.bias, *ps = p.post_scale, *pt = p.post_shift;
+    if (p.param_smem) {
+        // per-channel epilogue constants: one copy per CTA in shared memory
+        for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) {
+            sparam[i] = p.bias[i];
+            if (p.post_scale) {
+                sparam[p.n_total + i] = p.post_scale[i];
+                sparam[2 * p.n_total + i] = p.post_shift[i];
+            }
+        }
+        pb = sparam; ps = sparam + p.n_total; pt = sparam + 2 * p.n_total;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -177,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);
+            mbar_init(&tmem_empty[s], kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -253,75 +399,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
-            long long pix = -1;
-            if (p.spatial) {
-                const int per_img = p.tiles_x * p.tiles_y;
-                const int img = m_tile / per_img;
-                const int r = m_tile - img * per_img;
-                const int y = (r / p.tiles_x) * 8 + (row >> 4), x = (r % p.tiles_x) * 16 + (row & 15);
-                if (y < p.H && x < p.W) pix = (long long)img * p.H * p.W + (long long)y * p.W + x;
-            } else {
-                const long long m = (long long)m_tile * BLOCK_M + row;
-                if (m < p.M) pix = m;
-            }
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
-            const int ch0 = n_idx * p.n_chunk;
-            for (int c0 = 0; c0 < p.n_chunk; c0 += 16) {
-                if (ch0 + c0 >= p.n_store) break;   // warp-uniform
-                uint32_t raw[16];
-                tmem_ld16(taddr + uint32_t(c0), raw);     // .sync.aligned: executed by the whole (converged) warp
-                if (pix >= 0) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int ch = ch0 + c0 + j;
-                        float x = __uint_as_float(raw[j]);
-                        if (ch < p.n_store) {
-                            x += p.bias[ch];
-                            x = tc_act(x, p.act, p.hs_slope, p.hs_offset);
-                            if (p.post_scale) x = x * p.post_scale[ch] + p.post_shift[ch];
-                        }
-                        v[j] = x;
-                    }
-                    __half* o = static_cast<__half*>(p.out) + size_t(pix) * p.out_cs + ch0 + c0;
-#pragma unroll
-                    for (int h8 = 0; h8 < 2; h8++) {
-                        if (ch0 + c0 + h8 * 8 >= p.n_store) break;
-                        if (p.res) {
-                            const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + size_t(pix) * p.res_cs + ch0 + c0 + h8 * 8);
-                            const __half2* rh = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const float2 f = __half22float2(rh[j]);
-                                v[h8 * 8 + 2 * j] += f.x;
-                                v[h8 * 8 + 2 * j + 1] += f.y;
-                            }
-                        }
-                        uint4 u;
-                        __half2* hh = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            hh[j] = __floats2half2_rn(tc_act(v[h8 * 8 + 2 * j], p.act2, 0.f, 0.f), tc_act(v[h8 * 8 + 2 * j + 1], p.act2, 0.f, 0.f));
-                        *reinterpret_cast<uint4*>(o + h8 * 8) = u;
-                    }
-                }
-                __syncwarp();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
-        }
+        // ---------------- epilogue: warps 2..9 ----------------
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        if (p.post_scale) epilogue_dispatch<true>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane);
+        else epilogue_dispatch<false>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -434,7 +515,10 @@ void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
     p.kh = t.kh; p.kw = t.kw; p.ph = t.ph; p.pw = t.pw; p.num_kb = t.num_kb; p.k_pad = t.k_pad;
     p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = t.num_m_tiles;
     const int stage_bytes = A_BYTES + t.n_chunk * 128;
-    const int budget = kMaxSmem - 2048;
+    p.n_total = t.n_chunk * t.n_chunks;
+    p.param_smem = p.n_total <= kParamSmemMaxCh ? 1 : 0;
+    const int param_bytes = p.param_smem ? 3 * p.n_total * int(sizeof(float)) : 0;
+    const int budget = kMaxSmem - 2048 - param_bytes;
     p.stages = std::max(2, std::min(8, budget / stage_bytes));
     int cols = 32;
     while (cols < 2 * t.n_chunk) cols *= 2;
@@ -443,7 +527,7 @@ void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
     p.bias = t.epi.bias; p.post_scale = t.epi.post_scale; p.post_shift = t.epi.post_shift;
     p.res = t.epi.res; p.res_cs = t.epi.res_cs; p.act = t.epi.act; p.act2 = t.epi.act2;
     p.hs_slope = t.epi.hs_slope; p.hs_offset = t.epi.hs_offset;
-    const size_t smem = size_t(p.stages) * stage_bytes + 1024 + 256;
+    const size_t smem = size_t(p.stages) * stage_bytes + 1024 + 256 + param_bytes;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);

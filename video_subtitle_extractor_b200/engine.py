@@ -19,6 +19,7 @@ PLAN_DET, PLAN_REC = 0, 1
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
 PRECISION_FP16, PRECISION_FP32 = 0, 1
 FLAG_NO_TENSOR_CORES = 1
+FLAG_NO_FAST_KERNELS = 2
 
 
 class VseConfig(C.Structure):
