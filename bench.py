@@ -288,7 +288,14 @@ def run_b200(args, rank, local_rank, world):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    def prefetch(batches, k):
+        base = batches[k % len(batches)].data_ptr()
+        eng.prefetch([base + j * frame_bytes for j in range(B)], hs, ws, None, mem_kind=E.MEM_PINNED)
+
     def timed(batches, mem_kind):
+        # host-resident batches: the copy of step k+1 is issued (vse_prefetch, copy stream) before step k runs, so every
+        # step's host->device copy is inside the timed region but overlaps the previous step's kernels
+        pf = mem_kind != E.MEM_DEVICE
         for k in range(args.warmup):
             step(batches, k, mem_kind)
         barrier()
@@ -296,7 +303,11 @@ def run_b200(args, rank, local_rank, world):
         l0 = eng.launch_count
         t0 = time.perf_counter()
         n_lines = 0
+        if pf:
+            prefetch(batches, 0)
         for k in range(args.steps):
+            if pf and k + 1 < args.steps:
+                prefetch(batches, k + 1)
             res = step(batches, k, mem_kind)
             dev_ms += float(eng.last_timings[7])
             n_lines += sum(len(r.quads) for r in res)

@@ -47,7 +47,10 @@ enum { VSE_PLAN_DET = 0, VSE_PLAN_REC = 1 };
 enum { VSE_PRECISION_FP16 = 0, VSE_PRECISION_FP32 = 1 };
 enum {
     VSE_FLAG_NO_TENSOR_CORES = 1, /* vse_config.flags: keep every conv on the CUDA-core kernels (A/B checks)      */
-    VSE_FLAG_NO_FAST_KERNELS = 2  /* keep depthwise / stem / DB-head steps on the generic kernels (A/B checks)     */
+    VSE_FLAG_NO_FAST_KERNELS = 2, /* keep depthwise / stem / DB-head / SE steps on the generic kernels (A/B checks) */
+    /* finer A/B switches (bisecting numerical differences); each disables one specialised path */
+    VSE_FLAG_NO_FUSED_HEAD = 4, VSE_FLAG_NO_SE_FUSION = 8, VSE_FLAG_NO_ROWBOX = 16, VSE_FLAG_NO_FAST_DW = 32,
+    VSE_FLAG_NO_FAST_STEM = 64
 };
 
 /* Mirrors the knobs the reference passes to PaddleOCR / TextDetector (ocr.py:91-113) and the
@@ -97,6 +100,14 @@ int  vse_load_plan(vse_engine* e, int32_t which, const void* blob, size_t nbytes
  * TextSystem order: boxes sorted top-to-bottom / left-to-right per frame. */
 int  vse_run(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const int32_t* w,
              const int32_t* row_stride, int32_t n_frames, int32_t mem_kind, vse_result* out);
+
+/* Optional: start the host->device copy of the NEXT batch (pinned or pageable host frames) on the engine's copy stream
+ * and return at once, so that it overlaps the vse_run of the current batch.  The next vse_run / vse_det_only called with
+ * the same frame pointers, sizes and strides uses the staged copy; any other call simply ignores it.  The host frames
+ * must stay valid and unchanged until that call returns.  The reference has no counterpart (it feeds one frame per call,
+ * backend/tools/subtitle_ocr.py:30); its producer thread (:164-208) is where a caller would issue this. */
+int  vse_prefetch(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const int32_t* w,
+                  const int32_t* row_stride, int32_t n_frames, int32_t mem_kind);
 
 /* det only: TextDetector order (contour order), quads/det_score/n_boxes filled. */
 int  vse_det_only(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const int32_t* w,

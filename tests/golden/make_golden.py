@@ -19,7 +19,7 @@ from oracle.pipeline import OraclePipeline  # noqa: E402
 
 REF = "/root/reference"
 OUT = os.path.dirname(os.path.abspath(__file__))
-CASES = [("test_en.mp4", [300, 1500, 2500]), ("test_cn.mp4", [600])]
+CASES = [("test_en.mp4", [300, 600, 900, 1200, 1500, 1800, 2100, 2500, 3000, 3300]), ("test_cn.mp4", [600, 1000])]
 
 
 def main():

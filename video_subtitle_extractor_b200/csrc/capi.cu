@@ -103,6 +103,12 @@ int vse_run(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const
     return guarded(e, [&] { e->impl->run_frames(frames, h, w, row_stride, n_frames, mem_kind, out, false); });
 }
 
+int vse_prefetch(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* row_stride,
+                 int32_t n_frames, int32_t mem_kind) {
+    if (!e || (n_frames > 0 && (!frames || !h || !w))) return VSE_ERR_INVALID;
+    return guarded(e, [&] { e->impl->prefetch_frames(frames, h, w, row_stride, n_frames, mem_kind); });
+}
+
 int vse_det_only(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* row_stride,
                  int32_t n_frames, int32_t mem_kind, vse_result* out) {
     if (!e || !out || (n_frames > 0 && (!frames || !h || !w))) return VSE_ERR_INVALID;

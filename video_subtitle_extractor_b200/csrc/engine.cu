@@ -340,8 +340,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
     pin_.reserve(ntab * sizeof(ImgTab));
     for (auto& g : cx.geos) std::memcpy(pin_.as<ImgTab>() + g.tab_off, g.tab.data(), g.tab.size() * sizeof(ImgTab));
     cx.tabs.reserve(ntab * sizeof(ImgTab));
-    VSE_CUDA(cudaMemcpyAsync(cx.tabs.p, pin_.p, ntab * sizeof(ImgTab), cudaMemcpyHostToDevice, stream));
-    VSE_CUDA(cudaStreamSynchronize(stream));  // pin_ is reused by the caller
+    launch_upload(cx.tabs.p, pin_.p, ntab * sizeof(ImgTab), stream);   // kernel-parameter upload: no copy engine, no sync
 
     // arena planning (first-fit free list over root buffers)
     struct Block { size_t off, size; };
@@ -425,7 +424,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         if (!flat && !(uniform && 2 * ph == kh - 1 && 2 * pw == kw - 1)) continue;
         const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_off[k];
         std::string why = tc_conv_setup(cx.tc[k], vptr(which, s.ins[0]), value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], flat,
-                                        gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw);
+                                        gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX));
         if (!why.empty()) cx.tc[k].valid = false;
     }
 }
@@ -535,12 +534,12 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 };
                 if (s.op == OP_DWCONV) {
                     if (out_f32) throw InvalidArg{"depthwise conv cannot produce a fetched output"};
-                    if (fast && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
+                    if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
                     else launch_dwconv(a, prec, stream);
                 } else if (s.op == OP_DECONV2) {
                     // DB head: deconv(C->C)+ReLU feeding only a deconv(C->1)+sigmoid that is a fetched fp32 map -> one kernel
                     bool fused = false;
-                    if (fast && !last_keep_all_[which] && k + 1 < pd.steps.size()) {
+                    if (fast && !(cfg.flags & VSE_FLAG_NO_FUSED_HEAD) && !last_keep_all_[which] && k + 1 < pd.steps.size()) {
                         const StepRec& s2 = pd.steps[k + 1];
                         const ValueRec& v2 = pd.values[s2.out];
                         if (s2.op == OP_DECONV2 && s2.ins[0] == s.out && pd.values[s.out].last_use == int(k + 1) &&
@@ -562,7 +561,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                     } else {
                         launch_deconv2(a, s.p[P_COUT], prec, stream);
                     }
-                } else if (s.op == OP_STEM && fast && launch_stem_fast(a, s.p[P_COUT], max_units(2), stream)) {
+                } else if (s.op == OP_STEM && fast && !(cfg.flags & VSE_FLAG_NO_FAST_STEM) && launch_stem_fast(a, s.p[P_COUT], max_units(2), stream)) {
                     cx.kind[k] = 2;
                 } else {
                     if (out_f32) a.cout_store = s.p[P_COUT];
@@ -574,10 +573,39 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
             case OP_GPOOL: {
                 const int cp = pad8(pd.values[s.ins[0]].channels);
                 const Geo& g = geo_of(s.ins[0]);
-                int splits = std::min(64, std::max(1, g.max_pix / 2048));
+                // enough CTAs to fill the machine (n_img x splits >= ~2 waves), at least 64 pixels per split
+                int splits = std::max(1, std::min({64, g.max_pix / 64, (2 * sm_count + cx.n_img - 1) / std::max(cx.n_img, 1)}));
                 float* partial = reinterpret_cast<float*>(static_cast<char*>(arena_[which].p) + cx.scratch_off);
-                launch_gpool(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), cp, tab_of(s.ins[0]), cx.n_img, g.max_pix, partial,
-                             splits, static_cast<float*>(ptr_of(s.out)), vo.channels, prec, stream);
+                // squeeze-excite: GPOOL -> VECLIN -> VECLIN (each the sole consumer of the previous) -> one gate kernel
+                bool fused = false;
+                if (prec == 0 && !(cfg.flags & (VSE_FLAG_NO_FAST_KERNELS | VSE_FLAG_NO_SE_FUSION)) && !last_keep_all_[which] && k + 2 < pd.steps.size()) {
+                    const StepRec& f1 = pd.steps[k + 1];
+                    const StepRec& f2 = pd.steps[k + 2];
+                    auto plain = [](const StepRec& f) { return !f.p[P_HAS_POST] && !f.p[P_HAS_RES] && f.p[P_ACT2] == ACT_NONE; };
+                    if (f1.op == OP_VECLIN && f2.op == OP_VECLIN && f1.ins[0] == s.out && f2.ins[0] == f1.out &&
+                        pd.values[s.out].last_use == int(k + 1) && pd.values[f1.out].last_use == int(k + 2) && plain(f1) &&
+                        plain(f2) && f1.p[P_CIN] == vo.channels && f2.p[P_CIN] == f1.p[P_COUT] && f2.p[P_COUT] == f1.p[P_CIN] &&
+                        lp.dev[k + 1].bias && lp.dev[k + 2].bias && f1.p[P_CIN] + f1.p[P_COUT] <= 8192) {
+                        launch_gpool_partial(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), cp, tab_of(s.ins[0]), cx.n_img, partial,
+                                             splits, prec, stream);
+                        launch_se_gate(partial, splits, cp, f1.p[P_CIN], f1.p[P_COUT], tab_of(s.ins[0]), lp.dev[k + 1].w,
+                                       lp.dev[k + 1].bias, f1.p[P_ACT], f1.f[F_HS_SLOPE], f1.f[F_HS_OFFSET], lp.dev[k + 2].w,
+                                       lp.dev[k + 2].bias, f2.p[P_ACT], f2.f[F_HS_SLOPE], f2.f[F_HS_OFFSET],
+                                       static_cast<float*>(ptr_of(f2.out)), cx.n_img, stream);
+                        fused = true;
+                    }
+                }
+                if (fused) {
+                    cx.kind[k] = 2;
+                    for (int j = 0; j < 2; j++) {
+                        k++;
+                        cx.kind[k] = 3;
+                        if (step_events) cudaEventRecord((*step_events)[k], stream);
+                    }
+                } else {
+                    launch_gpool(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), cp, tab_of(s.ins[0]), cx.n_img, g.max_pix, partial,
+                                 splits, static_cast<float*>(ptr_of(s.out)), vo.channels, prec, stream);
+                }
                 launches += 2;
                 break;
             }

@@ -140,6 +140,8 @@ class Engine {
     int64_t get_value(int which, int vid, float* out, int64_t cap, int32_t* channels);
     const void* value_ptr(int which, int vid, int* cs, const Geo** geo);
 
+    void prefetch_frames(const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* stride, int n,
+                         int mem_kind);
     void run_frames(const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* stride, int n,
                     int mem_kind, vse_result* out, bool det_only);
 

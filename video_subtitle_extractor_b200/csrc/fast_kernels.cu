@@ -332,4 +332,67 @@ bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, con
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// squeeze-excite gate: (partial channel sums of the global average pool) -> mean -> FC(C->Cm)+act1 -> FC(Cm->C)+act2,
+// one CTA per image.  Replaces gpool_final + 2 x veclin (3 launches of a latency-bound chain) by one.
+// ------------------------------------------------------------------------------------------------
+struct SeDev {
+    const float* partial; int splits, c_pad, c, cm;
+    const ImgTab* tin;
+    const float* w1; const float* b1; const float* w2; const float* b2;
+    int act1, act2; float slope1, offset1, slope2, offset2;
+    float* out;
+};
+
+__device__ __forceinline__ float act_rt(float x, int act, float slope, float offset) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(x, 0.f);
+        case ACT_HSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        case ACT_HSIGMOID: return fminf(fmaxf(x * slope + offset, 0.f), 1.f);
+        case ACT_SWISH: return x / (1.f + __expf(-x));
+        case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+        case ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
+        default: return x;
+    }
+}
+
+__global__ void __launch_bounds__(256) se_gate_kernel(SeDev p) {
+    extern __shared__ float sm[];
+    float* mean = sm;            // [c]
+    float* hid = sm + p.c;       // [cm]
+    const int img = blockIdx.x;
+    const float inv = 1.f / float(p.tin[img].h * p.tin[img].w);
+    for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < p.splits; k++) s += p.partial[(size_t(img) * p.splits + k) * p.c_pad + c];
+        mean[c] = s * inv;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int co = warp; co < p.cm; co += nw) {
+        const float* wr = p.w1 + size_t(co) * p.c;
+        float s = 0.f;
+        for (int i = lane; i < p.c; i += 32) s = fmaf(wr[i], mean[i], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hid[co] = act_rt(s + p.b1[co], p.act1, p.slope1, p.offset1);
+    }
+    __syncthreads();
+    for (int co = warp; co < p.c; co += nw) {
+        const float* wr = p.w2 + size_t(co) * p.cm;
+        float s = 0.f;
+        for (int i = lane; i < p.cm; i += 32) s = fmaf(wr[i], hid[i], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) p.out[size_t(img) * p.c + co] = act_rt(s + p.b2[co], p.act2, p.slope2, p.offset2);
+    }
+}
+
+void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, const ImgTab* tin, const float* w1,
+                    const float* b1, int act1, float slope1, float offset1, const float* w2, const float* b2, int act2,
+                    float slope2, float offset2, float* out, int n_img, cudaStream_t st) {
+    SeDev d{partial, splits, c_pad, c, cm, tin, w1, b1, w2, b2, act1, act2, slope1, offset1, slope2, offset2, out};
+    se_gate_kernel<<<n_img, 256, size_t(c + cm) * sizeof(float), st>>>(d);
+}
+
 }  // namespace vse

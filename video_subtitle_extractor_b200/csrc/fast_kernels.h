@@ -19,4 +19,9 @@ bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, con
                           float* out, int out_cs, const ImgTab* tin, const ImgTab* tout, int n_img, int max_in_pix,
                           cudaStream_t st);
 
+// squeeze-excite gate from the partial sums written by launch_gpool_partial (nn_kernels): mean -> FC+act -> FC+act
+void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, const ImgTab* tin, const float* w1,
+                    const float* b1, int act1, float slope1, float offset1, const float* w2, const float* b2, int act2,
+                    float slope2, float offset2, float* out, int n_img, cudaStream_t st);
+
 }  // namespace vse

@@ -16,6 +16,7 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.h"
@@ -26,12 +27,15 @@ static constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 static constexpr int kEpiWarps = 8;
 static constexpr int kThreads = 64 + 32 * kEpiWarps;
+static constexpr int kMaxAccStages = 8;         // TMEM accumulator ring (512 columns / n_chunk, at most 8)
+static constexpr int kBarRegion = 512;          // shared-memory bytes reserved for the mbarriers + TMEM slot
+static constexpr int kBResidentMax = 80 * 1024; // weight matrices up to this size stay in shared memory for the whole kernel
 static constexpr int kParamSmemMaxCh = 1024;   // bias/scale/shift of up to this many channels are staged in shared memory
 static constexpr int kMaxSmem = 227 * 1024;
 
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
-        stages, tmem_cols;
+        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total;
     void* out;
     int out_cs;
     const float* bias;
@@ -132,6 +136,33 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// the descriptor's high word is constant (SBO = 1024 B, version 1, SWIZZLE_128B); the low word is (addr >> 4) | LBO field
+static constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 da, {%1, %5};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -267,8 +298,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
 }
 
@@ -293,13 +323,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = A_BYTES + p.n_chunk * 128;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * stage_bytes);
+    // rowbox (KxK): one A box of 8 + kh - 1 image rows per (kx, k-block) serves all kh vertical taps; B holds their kh slices
+    const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.rowbox ? p.kh : 1);
+    const int stage_bytes = p.a_bytes + b_bytes;
+    uint8_t* bres = smem + size_t(p.stages) * stage_bytes;          // resident weights: [tap][k-block][n_chunk x 64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(bres + p.b_total);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* sparam = reinterpret_cast<float*>(smem + size_t(p.stages) * stage_bytes + 256);
+    uint64_t* tmem_empty = tmem_full + kMaxAccStages;
+    uint64_t* b_full = tmem_empty + kMaxAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+    float* sparam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kBarRegion);
     const float *pb = p.bias, *ps = p.post_scale, *pt = p.post_shift;
     if (p.param_smem) {
         // per-channel epilogue constants: one copy per CTA in shared memory
@@ -321,10 +355,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < p.acc_stages; s++) {
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], kEpiWarps);
         }
+        mbar_init(b_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, uint32_t(p.tmem_cols));
@@ -335,13 +370,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int total_tiles = p.num_m_tiles * p.n_chunks;
     const int taps = p.kh * p.kw;
-    const int k_iters = taps * p.num_kb;
+    const int k_iters = (p.rowbox ? p.kw : taps) * p.num_kb;
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             int stage = 0;
             uint32_t phase = 0;
+            if (p.b_resident) {
+                mbar_expect_tx(b_full, uint32_t(p.b_total));
+                for (int tp = 0; tp < taps; tp++)
+                    for (int kb = 0; kb < p.num_kb; kb++)
+                        tma_load_2d(bres + size_t(tp * p.num_kb + kb) * p.n_chunk * 128, &map_b, b_full, tp * p.k_pad + kb * BLOCK_K, 0);
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
                 int img = 0, y0 = 0, x0 = 0;
@@ -353,50 +394,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     x0 = (r % p.tiles_x) * 16;
                 }
                 for (int it = 0; it < k_iters; it++) {
-                    const int tap = it / p.num_kb, kb = it - tap * p.num_kb;
+                    const int tap = it / p.num_kb, kb = it - tap * p.num_kb;   // rowbox: tap = kx
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_expect_tx(&full[stage], uint32_t(stage_bytes));
                     uint8_t* a_dst = smem + size_t(stage) * stage_bytes;
-                    if (p.spatial) {
-                        const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                        tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 + kx - p.pw, y0 + ky - p.ph, img);
+                    if (p.rowbox) {
+                        tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 + tap - p.pw, y0 - p.ph, img);
+                        for (int ky = 0; ky < p.kh && !p.b_resident; ky++)
+                            tma_load_2d(a_dst + p.a_bytes + ky * p.n_chunk * 128, &map_b, &full[stage],
+                                        (ky * p.kw + tap) * p.k_pad + kb * BLOCK_K, n_idx * p.n_chunk);
                     } else {
-                        tma_load_2d(a_dst, &map_a, &full[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+                        if (p.spatial) {
+                            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                            tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 + kx - p.pw, y0 + ky - p.ph, img);
+                        } else {
+                            tma_load_2d(a_dst, &map_a, &full[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+                        }
+                        if (!p.b_resident)
+                            tma_load_2d(a_dst + p.a_bytes, &map_b, &full[stage], tap * p.k_pad + kb * BLOCK_K, n_idx * p.n_chunk);
                     }
-                    tma_load_2d(a_dst + A_BYTES, &map_b, &full[stage], tap * p.k_pad + kb * BLOCK_K, n_idx * p.n_chunk);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            const uint32_t idesc = (1u << 4) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        // ---------------- MMA issuer ----------------
+        // The whole warp walks the loop (warp-uniform control flow and addresses, so the descriptor arithmetic stays on the
+        // uniform datapath); one elected lane issues the tcgen05 instructions.  With N as small as 32 an MMA costs ~16
+        // tensor-pipe cycles, so every scalar instruction spent per MMA in this loop shows up in the kernel time.
+        const uint32_t idesc = (1u << 4) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        if (p.b_resident) {
+            mbar_wait(b_full, 0);
+            tc_fence_after();
+        }
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t bres_lo = umma_desc_lo(smem_u32(bres));
+        const uint32_t b_step = uint32_t(p.n_chunk * 8);                 // one [n_chunk x 64] weight slice, in 16-byte units
+        const int nky = p.rowbox ? p.kh : 1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + uint32_t(acc * p.n_chunk);
+            int kb = 0, tap_it = 0;
+            for (int it = 0; it < k_iters; it++) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + uint32_t(acc * p.n_chunk);
-                for (int it = 0; it < k_iters; it++) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + size_t(stage) * stage_bytes);
-                    const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                        umma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
-                                 (it | k) != 0 ? 1u : 0u);
+                const uint32_t a_lo = umma_desc_lo(smem_base + uint32_t(stage * stage_bytes));
+                const int ksteps = min(BLOCK_K / UMMA_K, (p.cin - kb * BLOCK_K + UMMA_K - 1) / UMMA_K);   // skip all-zero K tail
+                if (elect_one()) {
+                    for (int ky = 0; ky < nky; ky++) {
+                        const uint32_t a_ky = a_lo + uint32_t(ky * 128);   // next image row of the box: 16 px * 128 B
+                        const uint32_t b_ky = p.b_resident
+                            ? bres_lo + uint32_t((p.rowbox ? ky * p.kw + tap_it : tap_it) * p.num_kb + kb) * b_step
+                            : a_lo + uint32_t(p.a_bytes >> 4) + uint32_t(ky) * b_step;
+                        const uint32_t first = (it | ky) != 0 ? 1u : 0u;
+                        umma_f16_words(d_tmem, a_ky, b_ky, idesc, first);
+                        if (ksteps > 1) umma_f16_words(d_tmem, a_ky + 2, b_ky + 2, idesc, 1u);
+                        if (ksteps > 2) umma_f16_words(d_tmem, a_ky + 4, b_ky + 4, idesc, 1u);
+                        if (ksteps > 3) umma_f16_words(d_tmem, a_ky + 6, b_ky + 6, idesc, 1u);
                     }
-                    umma_commit(&empty[stage]);   // smem slot is free once these MMAs have read it
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    umma_commit(&empty[stage]);                            // smem slot is free once these MMAs have read it
+                    if (it == k_iters - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
                 }
-                umma_commit(&tmem_full[acc]);     // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                __syncwarp();
+                if (++kb == p.num_kb) { kb = 0; tap_it++; }
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
         // ---------------- epilogue: warps 2..9 ----------------
@@ -460,23 +528,35 @@ static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t
     EncodeTiledFn fn = encode_fn();
     if (!fn) return "cuTensorMapEncodeTiled unavailable";
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    static int promo = -1;   // tuning knob (profiling only): VSE_TC_L2PROMO = 0 none | 1 64B | 2 128B (default) | 3 256B
+    if (promo < 0) {
+        const char* e = getenv("VSE_TC_L2PROMO");
+        promo = e ? atoi(e) : 2;
+        if (promo < 0 || promo > 3) promo = 2;
+    }
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), base, dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")";
     return "";
 }
 
 std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
-                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw) {
+                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox) {
     t.valid = false;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (in_cs & 7)) return "activation view not 16-byte aligned";
     if (pixels <= 0) return "empty";
     t.kh = kh; t.kw = kw; t.ph = ph; t.pw = pw;
     t.k_pad = w.k_pad;
+    t.cin = cin;
+    t.rowbox = 0;
     t.num_kb = (cin + BLOCK_K - 1) / BLOCK_K;
     t.n_chunk = w.n_chunk;
     t.n_chunks = w.n_chunks;
+    // weights resident in shared memory when the whole (single-chunk) matrix is small: tiles then stream activations only
+    const int b_all = kh * kw * t.num_kb * w.n_chunk * 128;
+    t.b_resident = (w.n_chunks == 1 && b_all <= kBResidentMax) ? 1 : 0;
     std::string err;
     if (flat) {
         t.spatial = 0;
@@ -494,7 +574,12 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         t.num_m_tiles = n_img * t.tiles_x * t.tiles_y;
         cuuint64_t dims[4] = {cuuint64_t(cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(n_img)};
         cuuint64_t strides[3] = {cuuint64_t(in_cs) * 2, cuuint64_t(W) * in_cs * 2, cuuint64_t(H) * W * in_cs * 2};
-        cuuint32_t box[4] = {BLOCK_K, 16, 8, 1};
+        // rowbox: one box of 8 + kh - 1 rows per (kx, k-block) instead of one 8-row box per tap — kh x less L2->smem
+        // traffic for the activations.  Needs >= 3 pipeline stages of (box + kh weight slices) in shared memory.
+        const int a_box = (8 + kh - 1) * 16 * 128;
+        const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + kh * w.n_chunk * 128);
+        t.rowbox = (allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - 16384) ? 1 : 0;
+        cuuint32_t box[4] = {BLOCK_K, 16, cuuint32_t(t.rowbox ? 8 + kh - 1 : 8), 1};
         err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box);
     }
     if (!err.empty()) return err;
@@ -514,20 +599,28 @@ void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
     p.spatial = t.spatial; p.M = t.M; p.n_img = t.n_img; p.H = t.H; p.W = t.W; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
     p.kh = t.kh; p.kw = t.kw; p.ph = t.ph; p.pw = t.pw; p.num_kb = t.num_kb; p.k_pad = t.k_pad;
     p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = t.num_m_tiles;
-    const int stage_bytes = A_BYTES + t.n_chunk * 128;
+    p.cin = t.cin;
+    p.rowbox = t.rowbox;
+    p.a_bytes = t.rowbox ? (8 + t.kh - 1) * 16 * 128 : A_BYTES;
     p.n_total = t.n_chunk * t.n_chunks;
     p.param_smem = p.n_total <= kParamSmemMaxCh ? 1 : 0;
     const int param_bytes = p.param_smem ? 3 * p.n_total * int(sizeof(float)) : 0;
-    const int budget = kMaxSmem - 2048 - param_bytes;
+    p.b_resident = t.b_resident;
+    p.b_total = t.b_resident ? t.kh * t.kw * t.num_kb * t.n_chunk * 128 : 0;
+    const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.rowbox ? t.kh : 1));
+    const int budget = kMaxSmem - 1024 - kBarRegion - param_bytes - p.b_total;
     p.stages = std::max(2, std::min(8, budget / stage_bytes));
+    // TMEM accumulator ring: the MMA warp runs up to acc_stages tiles ahead of the epilogue (hides the commit -> wait ->
+    // tcgen05.ld -> arrive round trip, which dominates layers with one k-iteration per tile)
+    p.acc_stages = std::max(2, std::min(kMaxAccStages, 512 / t.n_chunk));
     int cols = 32;
-    while (cols < 2 * t.n_chunk) cols *= 2;
+    while (cols < p.acc_stages * t.n_chunk) cols *= 2;
     p.tmem_cols = cols;
     p.out = t.out; p.out_cs = t.out_cs;
     p.bias = t.epi.bias; p.post_scale = t.epi.post_scale; p.post_shift = t.epi.post_shift;
     p.res = t.epi.res; p.res_cs = t.epi.res_cs; p.act = t.epi.act; p.act2 = t.epi.act2;
     p.hs_slope = t.epi.hs_slope; p.hs_offset = t.epi.hs_offset;
-    const size_t smem = size_t(p.stages) * stage_bytes + 1024 + 256 + param_bytes;
+    const size_t smem = size_t(p.stages) * stage_bytes + p.b_total + 1024 + kBarRegion + param_bytes;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);

@@ -30,6 +30,9 @@ struct TcConv {
     int M = 0;              // flat: number of pixels
     int n_img = 0, H = 0, W = 0, tiles_x = 0, tiles_y = 0;
     int kh = 1, kw = 1, ph = 0, pw = 0;
+    int cin = 0;            // real input channels (the MMA loop skips the all-zero tail of the last K block)
+    int rowbox = 0;         // KxK: A boxes span 8 + kh - 1 image rows and serve all vertical taps (see gemm_tc.cu)
+    int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
     int num_kb = 1;         // 64-channel K blocks per tap
     int k_pad = 64;
     int n_chunk = 16, n_chunks = 1, n_store = 8;
@@ -43,7 +46,7 @@ struct TcConv {
 // Fills map_a/map_b + tile counts. `in`: activation base (fp16, channel stride in_cs), `wdev`: packed weights on device.
 // Returns an empty string on success, else the reason the step cannot use the tensor-core path.
 std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
-                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw);
+                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox = true);
 
 void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st);
 

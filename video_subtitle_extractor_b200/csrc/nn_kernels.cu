@@ -11,6 +11,7 @@
 
 #include <cuda_fp16.h>
 #include <cfloat>
+#include <cstring>
 
 #include "plan.h"
 
@@ -404,11 +405,16 @@ __global__ void gpool_final_kernel(const float* partial, int splits, int c_pad, 
     }
 }
 
-void launch_gpool(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n_img, int max_pix, float* partial,
-                  int splits, float* out, int out_c, int prec, cudaStream_t st) {
+void launch_gpool_partial(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n_img, float* partial, int splits,
+                          int prec, cudaStream_t st) {
     dim3 grid(splits, n_img);
     if (prec == 0) gpool_partial_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), in_cs, c_pad / 8, tin, partial, splits);
     else gpool_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), in_cs, c_pad / 8, tin, partial, splits);
+}
+
+void launch_gpool(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n_img, int max_pix, float* partial,
+                  int splits, float* out, int out_c, int prec, cudaStream_t st) {
+    launch_gpool_partial(in, in_cs, c_pad, tin, n_img, partial, splits, prec, st);
     gpool_final_kernel<<<n_img, 128, 0, st>>>(partial, splits, c_pad, tin, out, out_c);
     (void)max_pix;
 }
@@ -807,6 +813,29 @@ void launch_to_float(const void* in, int in_cs, int dtype_is_f32, float* out, in
     int grid = cdiv(pixels * c, 256);
     if (dtype_is_f32 || prec == 1) to_float_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, out, c, pixels);
     else to_float_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, out, c, pixels);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small host -> device tables (job lists, image tables): carried in the kernel PARAMETERS instead of a
+// cudaMemcpyAsync, so they never queue on the copy engine behind a multi-megabyte frame prefetch, and the host
+// buffer is free again as soon as the launch call returns.
+// ------------------------------------------------------------------------------------------------
+struct UploadBlob { uint32_t w[1000]; };
+__global__ void upload_kernel(UploadBlob b, uint32_t* dst, int nwords) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = b.w[i];
+}
+
+int launch_upload(void* dst, const void* src_host, size_t bytes, cudaStream_t st) {
+    const size_t chunk = sizeof(UploadBlob);
+    int n = 0;
+    for (size_t off = 0; off < bytes; off += chunk, n++) {
+        UploadBlob b;
+        const size_t m = bytes - off < chunk ? bytes - off : chunk;
+        std::memcpy(b.w, static_cast<const char*>(src_host) + off, m);
+        // destination buffers are DevBuf allocations (256-byte slack): rounding the tail up to 4 bytes stays inside
+        upload_kernel<<<1, 256, 0, st>>>(b, reinterpret_cast<uint32_t*>(static_cast<char*>(dst) + off), int((m + 3) / 4));
+    }
+    return n;
 }
 
 }  // namespace vse

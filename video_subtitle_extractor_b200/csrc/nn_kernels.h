@@ -48,6 +48,9 @@ void launch_deconv2(const ConvArgs& a, int cout, int prec, cudaStream_t st);
 
 void launch_gpool(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n_img, int max_pix, float* partial,
                   int splits, float* out, int out_c, int prec, cudaStream_t st);
+// first stage only: partial[img][split][c_pad] channel sums (deterministic; the caller finishes the reduction)
+void launch_gpool_partial(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n_img, float* partial, int splits,
+                          int prec, cudaStream_t st);
 void launch_veclin(const float* in, int cin, float* out, int cout, const float* w, const Epilogue& epi, int n_img,
                    cudaStream_t st);
 void launch_chscale(const void* in, int in_cs, void* out, int out_cs, int c_pad, const float* scale, int scale_c,
@@ -75,5 +78,8 @@ void launch_to_float(const void* in, int in_cs, int dtype_is_f32, float* out, in
                      cudaStream_t st);
 
 int attention_smem_bytes(int max_t, int dim);
+
+// host table -> device through kernel parameters (no copy-engine traffic); returns the number of launches
+int launch_upload(void* dst, const void* src_host, size_t bytes, cudaStream_t st);
 
 }  // namespace vse

@@ -16,7 +16,18 @@
 namespace vse {
 
 struct Engine::Pipeline {
-    DevBuf frames, det_in, jobs, det_frames;
+    // frame staging is double-buffered: vse_prefetch copies later batches (copy stream) into the buffer that no pending
+    // prefetch occupies while the current batch computes.  vse_run is synchronous, so a buffer is free as soon as the
+    // run that used it has returned.
+    struct Pending {
+        int buf;
+        std::vector<const uint8_t*> src, dev;
+        std::vector<int> h, w, stride;
+    };
+    DevBuf fbuf[2], dbg_frames, det_in, jobs, det_frames;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t fdone[2] = {nullptr, nullptr};
+    std::vector<Pending> pending;             // oldest first, at most 2
     DevBuf labels, slot_of, n_comp, roots, bbox, order, cand, status, n_boxes, quads, scores;
     DevBuf cubic_tab, crop_jobs, crop_buf, rec_jobs, rec_in;
     DevBuf ctc_meta, ctc_ids, ctc_len, ctc_score;
@@ -24,7 +35,7 @@ struct Engine::Pipeline {
     cudaEvent_t ev[9] = {};
     bool ev_ready = false, tab_ready = false;
     std::vector<DevBuf*> all() {
-        return {&frames, &det_in, &jobs, &det_frames, &labels, &slot_of, &n_comp, &roots, &bbox, &order, &cand, &status,
+        return {&fbuf[0], &fbuf[1], &dbg_frames, &det_in, &jobs, &det_frames, &labels, &slot_of, &n_comp, &roots, &bbox, &order, &cand, &status,
                 &n_boxes, &quads, &scores, &cubic_tab, &crop_jobs, &crop_buf, &rec_jobs, &rec_in, &ctc_meta, &ctc_ids,
                 &ctc_len, &ctc_score};
     }
@@ -44,6 +55,9 @@ Engine::~Engine() {
         pipe_->h_out.release();
         if (pipe_->ev_ready)
             for (auto& e : pipe_->ev) cudaEventDestroy(e);
+        for (auto& e : pipe_->fdone)
+            if (e) cudaEventDestroy(e);
+        if (pipe_->copy_stream) cudaStreamDestroy(pipe_->copy_stream);
         delete pipe_;
     }
     if (stream) cudaStreamDestroy(stream);
@@ -80,6 +94,10 @@ void Engine::ensure_pipeline() {
     if (!pipe_->ev_ready) {
         for (auto& e : pipe_->ev) VSE_CUDA(cudaEventCreate(&e));
         pipe_->ev_ready = true;
+    }
+    if (!pipe_->copy_stream) {
+        VSE_CUDA(cudaStreamCreateWithFlags(&pipe_->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : pipe_->fdone) VSE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     if (!pipe_->tab_ready) {
         std::vector<short> tab(32 * 32 * 16);
@@ -134,7 +152,7 @@ void Engine::db_post_device(const float* prob, const std::vector<DetFrame>& fram
     P->det_frames.reserve(n * sizeof(DetFrame));
     P->h_in.reserve(n * sizeof(DetFrame));
     std::memcpy(P->h_in.p, frames.data(), n * sizeof(DetFrame));
-    VSE_CUDA(cudaMemcpyAsync(P->det_frames.p, P->h_in.p, n * sizeof(DetFrame), cudaMemcpyHostToDevice, stream));
+    launch_upload(P->det_frames.p, P->h_in.p, n * sizeof(DetFrame), stream);
     DbParams dp{cfg.det_thresh, cfg.det_box_thresh, cfg.det_unclip_ratio, mc, mb, reading_order ? 1 : 0};
     launch_db_postprocess(prob, P->det_frames.as<DetFrame>(), frames.data(), n, max_rh, max_rw, dp, make_ws(P), stream, &launches);
     VSE_CUDA(cudaGetLastError());
@@ -157,6 +175,58 @@ void Engine::db_post_device(const float* prob, const std::vector<DetFrame>& fram
 // ------------------------------------------------------------------------------------------------
 // vse_run / vse_det_only
 // ------------------------------------------------------------------------------------------------
+static void frame_strides(const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* stride, int n,
+                          std::vector<int>& fstride) {
+    for (int i = 0; i < n; i++) {
+        if (h[i] <= 0 || w[i] <= 0 || !frames[i]) throw InvalidArg{"empty frame"};
+        if (h[i] + w[i] < 64) throw InvalidArg{"frame smaller than 64 px in total is not supported"};
+        fstride[i] = stride && stride[i] > 0 ? stride[i] : w[i] * 3;
+        if (fstride[i] < w[i] * 3) throw InvalidArg{"row stride smaller than 3*width"};
+    }
+}
+
+// host frames -> one staging buffer, 256-byte aligned slots, async on `st`
+static void stage_frames(const uint8_t* const* frames, const int32_t* h, const std::vector<int>& fstride, int n, DevBuf& buf,
+                         cudaStream_t st, std::vector<const uint8_t*>& fdev) {
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += (size_t(h[i]) * fstride[i] + 255) & ~size_t(255);
+    buf.reserve(total);
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        const size_t bytes = size_t(h[i]) * fstride[i];
+        VSE_CUDA(cudaMemcpyAsync(buf.as<uint8_t>() + off, frames[i], bytes, cudaMemcpyHostToDevice, st));
+        fdev[i] = buf.as<uint8_t>() + off;
+        off += (bytes + 255) & ~size_t(255);
+    }
+}
+
+// vse_prefetch: start the host->device copy of the NEXT batch on the copy stream while the current vse_run computes.
+// The following vse_run / vse_det_only with the same frame pointers and sizes finds the frames resident.
+void Engine::prefetch_frames(const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* stride, int n,
+                             int mem_kind) {
+    if (n <= 0 || mem_kind == VSE_MEM_DEVICE) return;
+    if (mem_kind < VSE_MEM_HOST || mem_kind > VSE_MEM_DEVICE) throw InvalidArg{"bad mem_kind"};
+    ensure_pipeline();
+    Pipeline* P = pipe_;
+    std::vector<int> fstride(n);
+    frame_strides(frames, h, w, stride, n, fstride);
+    if (P->pending.size() >= 2) {                  // no free buffer: the oldest unused prefetch gives way
+        VSE_CUDA(cudaStreamSynchronize(P->copy_stream));
+        P->pending.erase(P->pending.begin());
+    }
+    Pipeline::Pending pe;
+    pe.buf = P->pending.empty() ? 0 : 1 - P->pending[0].buf;
+    pe.dev.assign(n, nullptr);
+    // growing the buffer frees the old allocation (implicit device sync); the run that last used it has returned
+    stage_frames(frames, h, fstride, n, P->fbuf[pe.buf], P->copy_stream, pe.dev);
+    VSE_CUDA(cudaEventRecord(P->fdone[pe.buf], P->copy_stream));
+    pe.src.assign(frames, frames + n);
+    pe.h.assign(h, h + n);
+    pe.w.assign(w, w + n);
+    pe.stride = fstride;
+    P->pending.push_back(std::move(pe));
+}
+
 void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* stride, int n, int mem_kind,
                         vse_result* out, bool det_only) {
     if (n < 0) throw InvalidArg{"negative frame count"};
@@ -171,29 +241,34 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
     const int mb = cfg.max_boxes_per_frame;
     VSE_CUDA(cudaEventRecord(P->ev[0], stream));
 
-    // 1. frames -> device
+    // 1. frames -> device (already there when vse_prefetch staged exactly this batch)
     std::vector<const uint8_t*> fdev(n);
     std::vector<int> fstride(n);
-    {
-        size_t total = 0;
-        for (int i = 0; i < n; i++) {
-            if (h[i] <= 0 || w[i] <= 0 || !frames[i]) throw InvalidArg{"empty frame"};
-            if (h[i] + w[i] < 64) throw InvalidArg{"frame smaller than 64 px in total is not supported"};
-            fstride[i] = stride && stride[i] > 0 ? stride[i] : w[i] * 3;
-            if (fstride[i] < w[i] * 3) throw InvalidArg{"row stride smaller than 3*width"};
-            total += (size_t(h[i]) * fstride[i] + 255) & ~size_t(255);
+    frame_strides(frames, h, w, stride, n, fstride);
+    if (mem_kind == VSE_MEM_DEVICE) {
+        for (int i = 0; i < n; i++) fdev[i] = frames[i];
+    } else {
+        int hit = -1;
+        for (size_t q = 0; q < P->pending.size() && hit < 0; q++) {
+            const Pipeline::Pending& pe = P->pending[q];
+            bool same = int(pe.src.size()) == n;
+            for (int i = 0; same && i < n; i++)
+                same = pe.src[i] == frames[i] && pe.h[i] == h[i] && pe.w[i] == w[i] && pe.stride[i] == fstride[i];
+            if (same) hit = int(q);
         }
-        if (mem_kind == VSE_MEM_DEVICE) {
-            for (int i = 0; i < n; i++) fdev[i] = frames[i];
+        if (hit >= 0) {
+            VSE_CUDA(cudaStreamWaitEvent(stream, P->fdone[P->pending[hit].buf], 0));
+            fdev = P->pending[hit].dev;
+            P->pending.erase(P->pending.begin() + hit);
         } else {
-            P->frames.reserve(total);
-            size_t off = 0;
-            for (int i = 0; i < n; i++) {
-                size_t bytes = size_t(h[i]) * fstride[i];
-                VSE_CUDA(cudaMemcpyAsync(P->frames.as<uint8_t>() + off, frames[i], bytes, cudaMemcpyHostToDevice, stream));
-                fdev[i] = P->frames.as<uint8_t>() + off;
-                off += (bytes + 255) & ~size_t(255);
+            int buf = 0;
+            if (P->pending.size() >= 2) {          // both buffers hold batches nobody asked for: drop them
+                VSE_CUDA(cudaStreamSynchronize(P->copy_stream));
+                P->pending.clear();
+            } else if (P->pending.size() == 1) {
+                buf = 1 - P->pending[0].buf;
             }
+            stage_frames(frames, h, fstride, n, P->fbuf[buf], stream, fdev);
         }
     }
     VSE_CUDA(cudaEventRecord(P->ev[1], stream));
@@ -216,8 +291,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         P->jobs.reserve(n * sizeof(ResizeJob));
         P->h_in.reserve(n * sizeof(ResizeJob));
         std::memcpy(P->h_in.p, jobs.data(), n * sizeof(ResizeJob));
-        VSE_CUDA(cudaMemcpyAsync(P->jobs.p, P->h_in.p, n * sizeof(ResizeJob), cudaMemcpyHostToDevice, stream));
-        VSE_CUDA(cudaStreamSynchronize(stream));  // h_in is reused below
+        launch_upload(P->jobs.p, P->h_in.p, n * sizeof(ResizeJob), stream);   // (kernel parameters: h_in is free again)
         dim3 grid((max_pix + 255) / 256, n);
         resize_bilinear_u8_kernel<<<grid, 256, 0, stream>>>(P->jobs.as<ResizeJob>(), P->det_in.as<uint8_t>(), max_pix);
         launches++;
@@ -364,8 +438,8 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         std::memcpy(P->h_in.as<char>() + cj_bytes, rj.data(), rj_bytes);
         P->crop_jobs.reserve(std::max<size_t>(cj_bytes, 16));
         P->rec_jobs.reserve(rj_bytes);
-        if (!cj.empty()) VSE_CUDA(cudaMemcpyAsync(P->crop_jobs.p, P->h_in.p, cj_bytes, cudaMemcpyHostToDevice, stream));
-        VSE_CUDA(cudaMemcpyAsync(P->rec_jobs.p, P->h_in.as<char>() + cj_bytes, rj_bytes, cudaMemcpyHostToDevice, stream));
+        if (!cj.empty()) launch_upload(P->crop_jobs.p, P->h_in.p, cj_bytes, stream);
+        launch_upload(P->rec_jobs.p, P->h_in.as<char>() + cj_bytes, rj_bytes, stream);
         if (!cj.empty()) {
             launch_crops(P->crop_jobs.as<CropJob>(), int(cj.size()), max_crop_pix, P->cubic_tab.as<short>(), P->crop_buf.as<uint8_t>(), stream);
             launches++;
@@ -402,7 +476,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         P->ctc_score.reserve(nC * sizeof(float));
         P->h_in.reserve(meta.size() * sizeof(int));
         std::memcpy(P->h_in.p, meta.data(), meta.size() * sizeof(int));
-        VSE_CUDA(cudaMemcpyAsync(P->ctc_meta.p, P->h_in.p, meta.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        launch_upload(P->ctc_meta.p, P->h_in.p, meta.size() * sizeof(int), stream);
         launch_ctc_decode(probs, C, P->ctc_meta.as<int>(), P->ctc_meta.as<int>() + nC, nC, max_t, P->ctc_ids.as<int>(),
                           P->ctc_len.as<int>(), P->ctc_score.as<float>(), stream);
         launches++;
@@ -456,11 +530,11 @@ void Engine::debug_run_plan(int which, const uint8_t* const* images, int n, int 
 void Engine::debug_resize(const uint8_t* src, int sh, int sw, int stride, uint8_t* dst, int dh, int dw) {
     ensure_pipeline();
     if (stride <= 0) stride = sw * 3;
-    pipe_->frames.reserve(size_t(sh) * stride);
+    pipe_->dbg_frames.reserve(size_t(sh) * stride);
     pipe_->det_in.reserve(size_t(dh) * dw * 4);
     pipe_->jobs.reserve(sizeof(ResizeJob));
-    VSE_CUDA(cudaMemcpyAsync(pipe_->frames.p, src, size_t(sh) * stride, cudaMemcpyHostToDevice, stream));
-    ResizeJob j{pipe_->frames.as<uint8_t>(), sh, sw, stride, 3, dh, dw, dw, 0};
+    VSE_CUDA(cudaMemcpyAsync(pipe_->dbg_frames.p, src, size_t(sh) * stride, cudaMemcpyHostToDevice, stream));
+    ResizeJob j{pipe_->dbg_frames.as<uint8_t>(), sh, sw, stride, 3, dh, dw, dw, 0};
     VSE_CUDA(cudaMemcpyAsync(pipe_->jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice, stream));
     dim3 grid((dh * dw + 255) / 256, 1);
     resize_bilinear_u8_kernel<<<grid, 256, 0, stream>>>(pipe_->jobs.as<ResizeJob>(), pipe_->det_in.as<uint8_t>(), dh * dw);
@@ -495,9 +569,9 @@ void Engine::debug_crop(const uint8_t* frame, int h, int w, const float* quad, u
     j.rot90 = (j.ch * 1.0 / j.cw >= 1.5) ? 1 : 0;
     const int H = j.rot90 ? j.cw : j.ch, W = j.rot90 ? j.ch : j.cw;
     if (size_t(H) * W * 3 > size_t(cap)) throw CapacityError{"debug_crop: capacity too small"};
-    pipe_->frames.reserve(size_t(h) * w * 3);
-    VSE_CUDA(cudaMemcpyAsync(pipe_->frames.p, frame, size_t(h) * w * 3, cudaMemcpyHostToDevice, stream));
-    j.frame = pipe_->frames.as<uint8_t>();
+    pipe_->dbg_frames.reserve(size_t(h) * w * 3);
+    VSE_CUDA(cudaMemcpyAsync(pipe_->dbg_frames.p, frame, size_t(h) * w * 3, cudaMemcpyHostToDevice, stream));
+    j.frame = pipe_->dbg_frames.as<uint8_t>();
     j.fh = h; j.fw = w; j.stride = w * 3; j.pix = 3;
     geom::rect_to_quad_homography(q, j.cw, j.ch, j.M);
     j.dst_off = 0;

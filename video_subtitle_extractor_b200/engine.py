@@ -20,6 +20,7 @@ MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
 PRECISION_FP16, PRECISION_FP32 = 0, 1
 FLAG_NO_TENSOR_CORES = 1
 FLAG_NO_FAST_KERNELS = 2
+FLAG_NO_FUSED_HEAD, FLAG_NO_SE_FUSION, FLAG_NO_ROWBOX, FLAG_NO_FAST_DW, FLAG_NO_FAST_STEM = 4, 8, 16, 32, 64
 
 
 class VseConfig(C.Structure):
@@ -37,7 +38,7 @@ class VseResult(C.Structure):
 
 
 EXPORTS = ["vse_default_config", "vse_abi_version", "vse_device_count", "vse_create", "vse_destroy", "vse_last_error",
-           "vse_load_plan", "vse_run", "vse_det_only", "vse_launch_count", "vse_tc_launch_count", "vse_debug_run_plan", "vse_debug_get_value",
+           "vse_load_plan", "vse_run", "vse_det_only", "vse_prefetch", "vse_launch_count", "vse_tc_launch_count", "vse_debug_run_plan", "vse_debug_get_value",
            "vse_debug_resize_bilinear", "vse_debug_db_postprocess", "vse_debug_crop", "vse_debug_time_steps"]
 
 
@@ -66,6 +67,7 @@ def load_library(path: Optional[str] = None):
     lib.vse_load_plan.argtypes = [vp, i32, vp, C.c_size_t]
     for fn in (lib.vse_run, lib.vse_det_only):
         fn.argtypes = [vp, pp_u8, p_i32, p_i32, p_i32, i32, i32, C.POINTER(VseResult)]
+    lib.vse_prefetch.argtypes = [vp, pp_u8, p_i32, p_i32, p_i32, i32, i32]
     lib.vse_launch_count.argtypes = [vp]
     lib.vse_launch_count.restype = i64
     lib.vse_tc_launch_count.argtypes = [vp]
@@ -195,6 +197,18 @@ class Engine:
         res, self.last_timings = self._run([f.ctypes.data for f in frames], [f.shape[0] for f in frames],
                                            [f.shape[1] for f in frames], [f.strides[0] for f in frames], MEM_HOST, det_only)
         return res
+
+    def prefetch(self, ptrs: Sequence[int], heights, widths, strides=None, mem_kind: int = MEM_PINNED):
+        """Start the host->device copy of the NEXT batch; the following run_device(...) with the same pointers uses it."""
+        n = len(ptrs)
+        if n == 0:
+            return
+        arr = (C.c_void_p * n)(*[int(p) for p in ptrs])
+        h, w = _i32(heights), _i32(widths)
+        st = _i32(strides) if strides is not None else None
+        as_p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(self.lib.vse_prefetch(self._h, arr, as_p(h), as_p(w), as_p(st) if st is not None else None, n, mem_kind),
+                    "vse_prefetch")
 
     def run_device(self, ptrs: Sequence[int], heights, widths, strides=None, det_only: bool = False, mem_kind: int = MEM_DEVICE):
         """frames already resident (device pointers, e.g. torch tensors' data_ptr()) or pinned host pointers."""
