@@ -60,7 +60,7 @@ void Engine::prepare_plan(LoadedPlan& lp) {
     const PlanData& pd = lp.data;
     std::vector<float> host;
     host.reserve(pd.weights.size() * 2 + 4096);
-    struct Off { size_t w = SIZE_MAX, bias = SIZE_MAX, ps = SIZE_MAX, pb = SIZE_MAX, g = SIZE_MAX, b = SIZE_MAX, sc = SIZE_MAX, sh = SIZE_MAX; };
+    struct Off { size_t bias_pk = SIZE_MAX, ps_pk = SIZE_MAX, pb_pk = SIZE_MAX, w = SIZE_MAX, bias = SIZE_MAX, ps = SIZE_MAX, pb = SIZE_MAX, g = SIZE_MAX, b = SIZE_MAX, sc = SIZE_MAX, sh = SIZE_MAX; };
     std::vector<Off> offs(pd.steps.size());
     lp.dev.assign(pd.steps.size(), StepDev{});
     auto alloc = [&](size_t nfloats) {
@@ -99,6 +99,29 @@ void Engine::prepare_plan(LoadedPlan& lp) {
                 if (s.p[P_HAS_POST]) {
                     o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, vec_pad);
                     o.pb = put_vec(pd.w(s, W_POST_SHIFT), cout, vec_pad);
+                }
+                // pixel-packed variant (gemm_tc.h): narrow 1x1 convs whose input pixels are 32 / 64 contiguous bytes and whose
+                // output is a dense value (not a slice of a concat buffer)
+                if (s.op == OP_CONV && kh == 1 && kw == 1 && s.p[P_SH] == 1 && s.p[P_SW] == 1 && s.p[P_PH] == 0 && s.p[P_PW] == 0 &&
+                    cfg.precision == VSE_PRECISION_FP16 && !(cfg.flags & (VSE_FLAG_NO_TENSOR_CORES | VSE_FLAG_NO_PIXEL_PACK)) &&
+                    s.ins[0] != pd.hdr.input_vid && pd.values[s.out].dtype != DT_F32) {
+                    const int ics = value_cs(pd, s.ins[0]), ocs = value_cs(pd, s.out);
+                    const bool res_ok = !s.p[P_HAS_RES] || value_cs(pd, s.ins[1]) == ocs;
+                    if ((ics == 16 || ics == 32) && cin <= ics && ocs == pad8(cout) && res_ok && (64 / ics) * ocs <= 1024) {
+                        d.pack = 64 / ics;
+                        const int n = d.pack * ocs, npad = n + 512;
+                        auto rep = [&](const float* src) -> size_t {
+                            size_t off = alloc(npad);
+                            for (int g = 0; g < d.pack; g++)
+                                for (int c = 0; c < cout; c++) host[off + size_t(g) * ocs + c] = src ? src[c] : 0.f;
+                            return off;
+                        };
+                        o.bias_pk = rep(pd.w(s, W_BIAS));
+                        if (s.p[P_HAS_POST]) {
+                            o.ps_pk = rep(pd.w(s, W_POST_SCALE));
+                            o.pb_pk = rep(pd.w(s, W_POST_SHIFT));
+                        }
+                    }
                 }
                 break;
             }
@@ -165,17 +188,28 @@ void Engine::prepare_plan(LoadedPlan& lp) {
     // fp16 K-major weight matrices for the tensor-core path
     lp.tcw.assign(pd.steps.size(), TcWeights{});
     lp.tcw_off.assign(pd.steps.size(), 0);
+    lp.tcw_pk.assign(pd.steps.size(), TcWeights{});
+    lp.tcw_pk_off.assign(pd.steps.size(), 0);
     if (cfg.precision == VSE_PRECISION_FP16 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
         std::vector<uint16_t> all;
+        auto append = [&](TcWeights& t) -> size_t {
+            while (all.size() % 512) all.push_back(0);   // 1024-byte aligned matrices
+            size_t off = all.size() * sizeof(uint16_t);
+            all.insert(all.end(), t.b.begin(), t.b.end());
+            t.b.clear();
+            t.b.shrink_to_fit();
+            return off;
+        };
         for (size_t k = 0; k < pd.steps.size(); k++) {
             const StepRec& s = pd.steps[k];
             if (s.op != OP_CONV || s.p[P_SH] != 1 || s.p[P_SW] != 1) continue;
             lp.tcw[k] = tc_pack_weights(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], s.p[P_KH] * s.p[P_KW]);
-            while (all.size() % 512) all.push_back(0);   // 1024-byte aligned matrices
-            lp.tcw_off[k] = all.size() * sizeof(uint16_t);
-            all.insert(all.end(), lp.tcw[k].b.begin(), lp.tcw[k].b.end());
-            lp.tcw[k].b.clear();
-            lp.tcw[k].b.shrink_to_fit();
+            lp.tcw_off[k] = append(lp.tcw[k]);
+            if (lp.dev[k].pack > 0) {
+                lp.tcw_pk[k] = tc_pack_weights_pixelpacked(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], value_cs(pd, s.ins[0]),
+                                                           value_cs(pd, s.out), lp.dev[k].pack);
+                lp.tcw_pk_off[k] = append(lp.tcw_pk[k]);
+            }
         }
         if (!all.empty()) {
             lp.tc_weights.reserve(all.size() * sizeof(uint16_t));
@@ -189,6 +223,7 @@ void Engine::prepare_plan(LoadedPlan& lp) {
         const Off& o = offs[k];
         d.w = ptr(o.w); d.bias = ptr(o.bias); d.post_scale = ptr(o.ps); d.post_shift = ptr(o.pb);
         d.gamma = ptr(o.g); d.beta = ptr(o.b); d.scale = ptr(o.sc); d.shift = ptr(o.sh);
+        d.bias_pk = ptr(o.bias_pk); d.post_scale_pk = ptr(o.ps_pk); d.post_shift_pk = ptr(o.pb_pk);
     }
 }
 
@@ -422,6 +457,14 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         bool uniform = true;
         for (auto& t : gi.tab) uniform = uniform && t.h == gi.tab[0].h && t.w == gi.tab[0].w;
         if (!flat && !(uniform && 2 * ph == kh - 1 && 2 * pw == kw - 1)) continue;
+        if (flat && lp.dev[k].pack > 0 && lp.tcw_pk[k].n_chunk > 0 && gi.total % lp.dev[k].pack == 0) {
+            // pixel-packed: `pack` pixels per GEMM row, K = 64, block-diagonal weights
+            const void* wpk = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_pk_off[k];
+            std::string why = tc_conv_setup(cx.tc[k], vptr(which, s.ins[0]), 64, 64, wpk, lp.tcw_pk[k], true, gi.total / lp.dev[k].pack,
+                                            cx.n_img, 1, 1, 1, 1, 0, 0, false);
+            cx.tc[k].pack = why.empty() ? lp.dev[k].pack : 0;
+            if (why.empty()) continue;
+        }
         const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_off[k];
         std::string why = tc_conv_setup(cx.tc[k], vptr(which, s.ins[0]), value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], flat,
                                         gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX));
@@ -747,9 +790,19 @@ bool Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
         t.out_cs = a.out_cs;
         t.n_store = a.cout_store;
         t.epi = a.epi;
-        launch_conv_tc(t, sm_count, stream);
-        tc_launches++;
-        return true;
+        if (t.pack > 0) {   // one GEMM row = `pack` consecutive pixels: their outputs (and residuals) are contiguous
+            const StepDev& d = plans_[which].dev[step];
+            t.out_cs = t.pack * a.out_cs;
+            t.n_store = t.pack * a.out_cs;
+            t.epi.bias = d.bias_pk;
+            if (a.epi.post_scale) { t.epi.post_scale = d.post_scale_pk; t.epi.post_shift = d.post_shift_pk; }
+            t.epi.res_cs = t.pack * a.epi.res_cs;
+        }
+        if (launch_conv_tc(t, sm_count, stream).empty()) {
+            tc_launches++;
+            return true;
+        }
+        t.valid = false;   // e.g. an output view the TMA store cannot address: CUDA-core kernel from now on
     }
     launch_conv_simt(a, prec, stream);
     return false;

@@ -88,6 +88,11 @@ struct StepDev {
     const float* scale = nullptr;
     const float* shift = nullptr;
     const void* w_tc = nullptr;  // half, K-major [cout_pad][k_pad] for the tensor-core path
+    // pixel-packed variant of a 1x1 conv (see Engine::load_plan): per-channel constants repeated `pack` times
+    const float* bias_pk = nullptr;
+    const float* post_scale_pk = nullptr;
+    const float* post_shift_pk = nullptr;
+    int pack = 0;                // pixels per packed GEMM row (0 = no packed variant)
     int w_ci = 0, w_co = 0, k_pad = 0, n_pad = 0;
 };
 
@@ -112,6 +117,8 @@ struct LoadedPlan {
     // tensor-core path: fp16 K-major weight matrices of the CONV steps (gemm_tc.cu)
     std::vector<TcWeights> tcw;      // per step (b emptied after upload; n_chunk == 0 => not packed)
     std::vector<size_t> tcw_off;     // byte offset into tc_weights
+    std::vector<TcWeights> tcw_pk;   // pixel-packed block-diagonal variants (n_chunk == 0 => none)
+    std::vector<size_t> tcw_pk_off;
     DevBuf tc_weights;
     bool loaded = false;
 };

@@ -30,6 +30,8 @@ static constexpr int kThreads = 64 + 32 * kEpiWarps;
 static constexpr int kMaxAccStages = 8;         // TMEM accumulator ring (512 columns / n_chunk, at most 8)
 static constexpr int kBarRegion = 512;          // shared-memory bytes reserved for the mbarriers + TMEM slot
 static constexpr int kBResidentMax = 80 * 1024; // weight matrices up to this size stay in shared memory for the whole kernel
+static constexpr int kOutBufs = 4;               // ring of [128 rows x 128 B] staging tiles for the TMA stores
+static constexpr int kOutBufBytes = BLOCK_M * 128;
 static constexpr int kParamSmemMaxCh = 1024;   // bias/scale/shift of up to this many channels are staged in shared memory
 static constexpr int kMaxSmem = 227 * 1024;
 
@@ -108,6 +110,26 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
             smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_16(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
@@ -216,9 +238,10 @@ __device__ __forceinline__ float tc_act(float x, int act, float slope, float off
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// 16 accumulator columns of one output pixel -> 16 fp16 values (two 16-byte pieces)
 template <int ACT, bool POST>
 __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* raw, const float* pb, const float* ps,
-                                            const float* pt, int cb, long long pix) {
+                                            const float* pt, int cb, long long pix, uint4* out2) {
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
@@ -233,12 +256,9 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* r
         }
         v[4 * j4 + 0] = x0; v[4 * j4 + 1] = x1; v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
     }
-    if (pix < 0) return;
-    __half* o = static_cast<__half*>(p.out) + size_t(pix) * p.out_cs + cb;
 #pragma unroll
     for (int h8 = 0; h8 < 2; h8++) {
-        if (cb + h8 * 8 >= p.n_store) break;
-        if (p.res) {
+        if (p.res && pix >= 0 && cb + h8 * 8 < p.n_store) {
             const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + size_t(pix) * p.res_cs + cb + h8 * 8);
             const __half2* rh = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
@@ -252,29 +272,37 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* r
 #pragma unroll
             for (int j = 0; j < 8; j++) v[h8 * 8 + j] = tc_act(v[h8 * 8 + j], p.act2, 0.f, 0.f);
         }
-        uint4 u;
-        __half2* hh = reinterpret_cast<__half2*>(&u);
+        __half2* hh = reinterpret_cast<__half2*>(&out2[h8]);
 #pragma unroll
         for (int j = 0; j < 4; j++) hh[j] = __floats2half2_rn(v[h8 * 8 + 2 * j], v[h8 * 8 + 2 * j + 1]);
-        *reinterpret_cast<uint4*>(o + h8 * 8) = u;
     }
 }
 
+// The 8 epilogue warps turn the accumulator into fp16 in 64-column sub-tiles: every thread writes its pixel's 32 columns
+// into a 128B-swizzled [128 pixels x 128 B] staging tile, the warps meet at a named barrier, and one thread hands the tile
+// to TMA (cp.async.bulk.tensor store): full-line, coalesced global writes, rows past the end of the tensor clipped by the
+// hardware.  A ring of kOutBufs staging tiles keeps kOutBufs - 1 stores in flight.
 template <int ACT, bool POST>
-__device__ __noinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
-                                           const float* pb, const float* ps, const float* pt, int q, int half, int lane) {
+__device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* map_o, uint8_t* sout, uint32_t tmem_base,
+                                           uint64_t* tmem_full, uint64_t* tmem_empty, const float* pb, const float* ps,
+                                           const float* pt, int q, int half, int lane, bool issuer) {
     const int row = q * 32 + lane;
     const int total_tiles = p.num_m_tiles * p.n_chunks;
-    int acc = 0;
+    const int n_sub = (p.n_chunk + 63) >> 6;
+    const uint32_t sout_addr = smem_u32(sout);
+    int acc = 0, slot = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
         long long pix = -1;
+        int img = 0, y0 = 0, x0 = 0;
         if (p.spatial) {
             const int per_img = p.tiles_x * p.tiles_y;
-            const int img = m_tile / per_img;
+            img = m_tile / per_img;
             const int r = m_tile - img * per_img;
-            const int y = (r / p.tiles_x) * 8 + (row >> 4), x = (r % p.tiles_x) * 16 + (row & 15);
+            y0 = (r / p.tiles_x) * 8;
+            x0 = (r % p.tiles_x) * 16;
+            const int y = y0 + (row >> 4), x = x0 + (row & 15);
             if (y < p.H && x < p.W) pix = (long long)img * p.H * p.W + (long long)y * p.W + x;
         } else {
             const long long m = (long long)m_tile * BLOCK_M + row;
@@ -284,50 +312,77 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
         const int ch0 = n_idx * p.n_chunk;
-        for (int c0 = half * 32; c0 < p.n_chunk; c0 += 64) {
-            if (ch0 + c0 >= p.n_store) break;   // warp-uniform
-            const bool two = c0 + 16 < p.n_chunk && ch0 + c0 + 16 < p.n_store;
-            uint32_t raw0[16], raw1[16];
-            tmem_ld16_nowait(taddr + uint32_t(c0), raw0);            // .sync.aligned: whole (converged) warp
-            if (two) tmem_ld16_nowait(taddr + uint32_t(c0 + 16), raw1);
-            tmem_ld_wait();
-            epi_chunk16<ACT, POST>(p, raw0, pb, ps, pt, ch0 + c0, pix);
-            if (two) epi_chunk16<ACT, POST>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix);
-            __syncwarp();
+        for (int sub = 0; sub < n_sub; sub++) {
+            if (ch0 + sub * 64 >= p.n_store) break;                    // uniform over the 8 warps
+            const int c0 = sub * 64 + half * 32;                        // this warp's 32 columns of the sub-tile
+            const uint32_t buf = sout_addr + uint32_t(slot * kOutBufBytes) + uint32_t(row * 128);
+            if (c0 < p.n_chunk && ch0 + c0 < p.n_store) {               // warp-uniform
+                const bool two = c0 + 16 < p.n_chunk && ch0 + c0 + 16 < p.n_store;
+                uint32_t raw0[16], raw1[16];
+                tmem_ld16_nowait(taddr + uint32_t(c0), raw0);           // .sync.aligned: whole (converged) warp
+                if (two) tmem_ld16_nowait(taddr + uint32_t(c0 + 16), raw1);
+                tmem_ld_wait();
+                uint4 o[2];
+                epi_chunk16<ACT, POST>(p, raw0, pb, ps, pt, ch0 + c0, pix, o);
+                const int j0 = half * 4;                                // 16-byte piece index inside the 128-byte row
+                st_shared_16(buf + uint32_t(((j0 + 0) ^ (row & 7)) << 4), o[0]);
+                st_shared_16(buf + uint32_t(((j0 + 1) ^ (row & 7)) << 4), o[1]);
+                if (two) {
+                    epi_chunk16<ACT, POST>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix, o);
+                    st_shared_16(buf + uint32_t(((j0 + 2) ^ (row & 7)) << 4), o[0]);
+                    st_shared_16(buf + uint32_t(((j0 + 3) ^ (row & 7)) << 4), o[1]);
+                }
+                fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA store
+            }
+            epi_barrier();
+            if (issuer) {
+                const void* src = sout + size_t(slot) * kOutBufBytes;
+                if (p.spatial) tma_store_4d(map_o, src, ch0 + sub * 64, x0, y0, img);
+                else tma_store_2d(map_o, src, ch0 + sub * 64, m_tile * BLOCK_M);
+                tma_store_commit();
+                tma_store_wait_read<kOutBufs - 2>();   // the tile written two barriers from now is free again (see ring note)
+            }
+            if (++slot == kOutBufs) slot = 0;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
+    if (issuer) tma_store_wait_all();
 }
 
 template <bool POST>
-__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
-                                                  const float* pb, const float* ps, const float* pt, int q, int half, int lane) {
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUtensorMap* map_o, uint8_t* sout, uint32_t tmem_base,
+                                                  uint64_t* tmem_full, uint64_t* tmem_empty, const float* pb, const float* ps,
+                                                  const float* pt, int q, int half, int lane, bool issuer) {
+#define VSE_EPI(A) epilogue_loop<A, POST>(p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer)
     switch (p.act) {
-        case ACT_RELU: epilogue_loop<ACT_RELU, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
-        case ACT_HSWISH: epilogue_loop<ACT_HSWISH, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
-        case ACT_HSIGMOID: epilogue_loop<ACT_HSIGMOID, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
-        case ACT_SWISH: epilogue_loop<ACT_SWISH, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
-        case ACT_SIGMOID: epilogue_loop<ACT_SIGMOID, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
-        case ACT_RELU6: epilogue_loop<ACT_RELU6, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
-        default: epilogue_loop<ACT_NONE, POST>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane); break;
+        case ACT_RELU: VSE_EPI(ACT_RELU); break;
+        case ACT_HSWISH: VSE_EPI(ACT_HSWISH); break;
+        case ACT_HSIGMOID: VSE_EPI(ACT_HSIGMOID); break;
+        case ACT_SWISH: VSE_EPI(ACT_SWISH); break;
+        case ACT_SIGMOID: VSE_EPI(ACT_SIGMOID); break;
+        case ACT_RELU6: VSE_EPI(ACT_RELU6); break;
+        default: VSE_EPI(ACT_NONE); break;
     }
+#undef VSE_EPI
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_o, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // rowbox (KxK): one A box of 8 + kh - 1 image rows per (kx, k-block) serves all kh vertical taps; B holds their kh slices
     const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.rowbox ? p.kh : 1);
     const int stage_bytes = p.a_bytes + b_bytes;
     uint8_t* bres = smem + size_t(p.stages) * stage_bytes;          // resident weights: [tap][k-block][n_chunk x 64]
-    uint64_t* full = reinterpret_cast<uint64_t*>(bres + p.b_total);
+    uint8_t* sout = bres + p.b_total;                               // kOutBufs staging tiles for the TMA stores
+    uint64_t* full = reinterpret_cast<uint64_t*>(sout + kOutBufs * kOutBufBytes);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
     uint64_t* tmem_empty = tmem_full + kMaxAccStages;
@@ -351,6 +406,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_o);
         for (int s = 0; s < p.stages; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -469,8 +525,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
         // ---------------- epilogue: warps 2..9 ----------------
         const int q = warp & 3, half = (warp - 2) >> 2;
-        if (p.post_scale) epilogue_dispatch<true>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane);
-        else epilogue_dispatch<false>(p, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane);
+        const bool issuer = threadIdx.x == 64;   // first epilogue thread: owns the bulk-store groups
+        if (p.post_scale) epilogue_dispatch<true>(p, &map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer);
+        else epilogue_dispatch<false>(p, &map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer);
     }
     tc_fence_before();
     __syncthreads();
@@ -490,7 +547,7 @@ TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps) {
     TcWeights t;
     const int n_mma = round_up_i(cout, 16);
     t.n_chunks = (n_mma + 255) / 256;
-    t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, 16);
+    t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, t.n_chunks > 1 ? 64 : 16);   // store boxes are 64 columns wide
     t.k_pad = round_up_i(cin, BLOCK_K);
     t.taps = taps;
     const size_t rows = size_t(t.n_chunks) * t.n_chunk, cols = size_t(taps) * t.k_pad;
@@ -502,6 +559,27 @@ TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps) {
                 uint16_t bits;
                 std::memcpy(&bits, &h, 2);
                 t.b[size_t(co) * cols + size_t(tp) * t.k_pad + ci] = bits;
+            }
+    return t;
+}
+
+TcWeights tc_pack_weights_pixelpacked(const float* w, int cout, int cin, int in_cs, int out_cs, int pack) {
+    TcWeights t;
+    const int n_real = pack * out_cs;
+    const int n_mma = round_up_i(n_real, 16);
+    t.n_chunks = (n_mma + 255) / 256;
+    t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, t.n_chunks > 1 ? 64 : 16);
+    t.k_pad = BLOCK_K;
+    t.taps = 1;
+    const size_t rows = size_t(t.n_chunks) * t.n_chunk, cols = BLOCK_K;
+    t.b.assign(rows * cols, 0);
+    for (int g = 0; g < pack; g++)
+        for (int co = 0; co < cout; co++)
+            for (int ci = 0; ci < cin; ci++) {
+                __half h = __float2half_rn(w[size_t(co) * cin + ci]);
+                uint16_t bits;
+                std::memcpy(&bits, &h, 2);
+                t.b[size_t(g * out_cs + co) * cols + size_t(g * in_cs + ci)] = bits;
             }
     return t;
 }
@@ -578,7 +656,7 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         // traffic for the activations.  Needs >= 3 pipeline stages of (box + kh weight slices) in shared memory.
         const int a_box = (8 + kh - 1) * 16 * 128;
         const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + kh * w.n_chunk * 128);
-        t.rowbox = (allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - 16384) ? 1 : 0;
+        t.rowbox = (allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - 16384 - kOutBufs * kOutBufBytes) ? 1 : 0;
         cuuint32_t box[4] = {BLOCK_K, 16, cuuint32_t(t.rowbox ? 8 + kh - 1 : 8), 1};
         err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box);
     }
@@ -594,7 +672,31 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
     return "";
 }
 
-void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
+// output tensor map (TMA stores): [n_store channels] x pixels, row pitch out_cs; re-encoded only when the target changes
+static std::string tc_output_map(TcConv& t) {
+    if (t.map_o_ptr == t.out && t.map_o_cs == t.out_cs && t.map_o_n == t.n_store) return "";
+    std::string err;
+    if (t.spatial) {
+        cuuint64_t dims[4] = {cuuint64_t(t.n_store), cuuint64_t(t.W), cuuint64_t(t.H), cuuint64_t(t.n_img)};
+        cuuint64_t strides[3] = {cuuint64_t(t.out_cs) * 2, cuuint64_t(t.W) * t.out_cs * 2, cuuint64_t(t.H) * t.W * t.out_cs * 2};
+        cuuint32_t box[4] = {BLOCK_K, 16, 8, 1};
+        err = encode(&t.map_o, t.out, 4, dims, strides, box);
+    } else {
+        cuuint64_t dims[2] = {cuuint64_t(t.n_store), cuuint64_t(t.M)};
+        cuuint64_t strides[1] = {cuuint64_t(t.out_cs) * 2};
+        cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
+        err = encode(&t.map_o, t.out, 2, dims, strides, box);
+    }
+    if (err.empty()) { t.map_o_ptr = t.out; t.map_o_cs = t.out_cs; t.map_o_n = t.n_store; }
+    return err;
+}
+
+std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & 7)) return "output view not 16-byte aligned";
+    {
+        std::string err = tc_output_map(t);
+        if (!err.empty()) return err;
+    }
     TcParams p{};
     p.spatial = t.spatial; p.M = t.M; p.n_img = t.n_img; p.H = t.H; p.W = t.W; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
     p.kh = t.kh; p.kw = t.kw; p.ph = t.ph; p.pw = t.pw; p.num_kb = t.num_kb; p.k_pad = t.k_pad;
@@ -608,7 +710,7 @@ void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
     p.b_resident = t.b_resident;
     p.b_total = t.b_resident ? t.kh * t.kw * t.num_kb * t.n_chunk * 128 : 0;
     const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.rowbox ? t.kh : 1));
-    const int budget = kMaxSmem - 1024 - kBarRegion - param_bytes - p.b_total;
+    const int budget = kMaxSmem - 1024 - kBarRegion - param_bytes - p.b_total - kOutBufs * kOutBufBytes;
     p.stages = std::max(2, std::min(8, budget / stage_bytes));
     // TMEM accumulator ring: the MMA warp runs up to acc_stages tiles ahead of the epilogue (hides the commit -> wait ->
     // tcgen05.ld -> arrive round trip, which dominates layers with one k-iteration per tile)
@@ -620,7 +722,7 @@ void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
     p.bias = t.epi.bias; p.post_scale = t.epi.post_scale; p.post_shift = t.epi.post_shift;
     p.res = t.epi.res; p.res_cs = t.epi.res_cs; p.act = t.epi.act; p.act2 = t.epi.act2;
     p.hs_slope = t.epi.hs_slope; p.hs_offset = t.epi.hs_offset;
-    const size_t smem = size_t(p.stages) * stage_bytes + p.b_total + 1024 + kBarRegion + param_bytes;
+    const size_t smem = size_t(p.stages) * stage_bytes + p.b_total + kOutBufs * kOutBufBytes + 1024 + kBarRegion + param_bytes;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -628,7 +730,8 @@ void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st) {
     }
     const int total = t.num_m_tiles * t.n_chunks;
     const int grid = std::max(1, std::min(total, sm_count));
-    conv_tc_kernel<<<grid, kThreads, smem, st>>>(t.map_a, t.map_b, p);
+    conv_tc_kernel<<<grid, kThreads, smem, st>>>(t.map_a, t.map_b, t.map_o, p);
+    return "";
 }
 
 }  // namespace vse

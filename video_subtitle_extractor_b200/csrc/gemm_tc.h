@@ -23,15 +23,25 @@ struct TcWeights {          // built once per plan step (host), uploaded as fp16
 // cout / cin: real channel counts; weights fp32 [cout][kh*kw][cin]
 TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps);
 
+// Pixel-packed 1x1 conv: `pack` consecutive pixels (channel stride in_cs, pack * in_cs == 64) form ONE GEMM row of K = 64
+// and the weights become block-diagonal [pack * out_cs][64]: row g*out_cs + co, column g*in_cs + ci = w[co][ci].  The
+// activation rows are then 128 bytes wide (TMA moves narrow 32/64-byte pixel rows at a fraction of its line rate) and the
+// `pack` output pixels of a row are contiguous in memory.
+TcWeights tc_pack_weights_pixelpacked(const float* w, int cout, int cin, int in_cs, int out_cs, int pack);
+
 struct TcConv {
     CUtensorMap map_a;      // activations (2-D flat for 1x1, 4-D [C][W][H][N] for KxK)
     CUtensorMap map_b;      // weights
+    CUtensorMap map_o;      // output (TMA stores), encoded lazily by launch_conv_tc
+    const void* map_o_ptr = nullptr;
+    int map_o_cs = 0, map_o_n = 0;
     int spatial = 0;        // 0: 1x1 over a flat pixel list; 1: KxK stride 1 over equal-sized images
     int M = 0;              // flat: number of pixels
     int n_img = 0, H = 0, W = 0, tiles_x = 0, tiles_y = 0;
     int kh = 1, kw = 1, ph = 0, pw = 0;
     int cin = 0;            // real input channels (the MMA loop skips the all-zero tail of the last K block)
     int rowbox = 0;         // KxK: A boxes span 8 + kh - 1 image rows and serve all vertical taps (see gemm_tc.cu)
+    int pack = 0;           // >0: pixel-packed flat conv (rows of `pack` pixels)
     int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
     int num_kb = 1;         // 64-channel K blocks per tap
     int k_pad = 64;
@@ -48,6 +58,7 @@ struct TcConv {
 std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
                           int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox = true);
 
-void launch_conv_tc(const TcConv& t, int sm_count, cudaStream_t st);
+// returns an empty string on success, else why the launch was not possible (nothing launched)
+std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st);
 
 }  // namespace vse
