@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace vse {
@@ -577,7 +578,11 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 };
                 if (s.op == OP_DWCONV) {
                     if (out_f32) throw InvalidArg{"depthwise conv cannot produce a fetched output"};
-                    if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
+                    static const int dw_mode = [] { const char* e = getenv("VSE_DW_MODE"); return e ? atoi(e) : 1; }();   // 0 strip, 1 tiled
+                    int mh = 0, mw = 0;
+                    for (const ImgTab& t : geo_of(s.out).tab) { mh = std::max(mh, t.h); mw = std::max(mw, t.w); }
+                    if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && dw_mode == 1 && launch_dwconv_tiled(a, mh, mw, stream)) cx.kind[k] = 2;
+                    else if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
                     else launch_dwconv(a, prec, stream);
                 } else if (s.op == OP_DECONV2) {
                     // DB head: deconv(C->C)+ReLU feeding only a deconv(C->1)+sigmoid that is a fetched fp32 map -> one kernel

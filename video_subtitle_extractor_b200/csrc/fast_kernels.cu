@@ -162,6 +162,160 @@ bool launch_dwconv_fast(const ConvArgs& a, int max_strip_units, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------------
+// depthwise KxK, shared-memory tiled: a CTA stages the input tile of (TH x 16 outputs) x (CBV * 8 channels) with
+// cp.async (every thread issues its 16-byte pieces back to back, out-of-image pieces are zero-filled = the padding),
+// waits once, and computes strips of 4 outputs from shared memory.  The strip kernel above pays a dependent global-load
+// round trip per filter row; on the small, L2-resident maps of the deep stages that latency is the whole run time.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int K, int SH, int SW, int TH, int CBV, int ACT>
+__global__ void __launch_bounds__(TH * 4 * CBV) dwconv_tile_kernel(DwDev p, int tiles_x) {
+    constexpr int TW = 16, ST = 4;                       // 16 output columns per tile, strips of 4
+    constexpr int IH = (TH - 1) * SH + K, IWT = (TW - 1) * SW + K;
+    constexpr int NT = TH * 4 * CBV;
+    extern __shared__ __align__(16) unsigned char dw_smem[];
+    __half* sin = reinterpret_cast<__half*>(dw_smem);                                   // [IH][IWT][CBV * 8]
+    float* sw = reinterpret_cast<float*>(dw_smem + size_t(IH) * IWT * CBV * 16);        // [K*K][CBV * 8]
+    const int img = blockIdx.y;
+    const ImgTab ti = p.tin[img], to = p.tout[img];
+    const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW;
+    if (ty0 >= to.h || tx0 >= to.w) return;
+    const int cv0 = blockIdx.z * CBV;
+    const int ncv = min(CBV, p.cvecs - cv0);
+    const int iy0 = ty0 * SH - p.ph, ix0 = tx0 * SW - p.pw;
+    const uint32_t sin_addr = (uint32_t)__cvta_generic_to_shared(sin);
+    for (int i = threadIdx.x; i < IH * IWT * CBV; i += NT) {
+        const int cv = i % CBV, pix = i / CBV;
+        const int r = pix / IWT, c = pix - r * IWT;
+        const int iy = iy0 + r, ix = ix0 + c;
+        const bool ok = cv < ncv && iy >= 0 && iy < ti.h && ix >= 0 && ix < ti.w;
+        const __half* src = ok ? p.in + (size_t(ti.off) + size_t(iy) * ti.w + ix) * p.in_cs + (cv0 + cv) * 8 : p.in;
+        cp_async_16(sin_addr + uint32_t(i) * 16, src, ok);
+    }
+    for (int i = threadIdx.x; i < K * K * CBV * 8; i += NT) {
+        const int c = i % (CBV * 8), t = i / (CBV * 8);
+        sw[i] = (cv0 * 8 + c < p.cp) ? p.w[size_t(t) * p.cp + cv0 * 8 + c] : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int cv = threadIdx.x % CBV;
+    const int st = (threadIdx.x / CBV) % 4, oyl = threadIdx.x / (CBV * 4);
+    const int oy = ty0 + oyl, ox0 = tx0 + st * ST;
+    if (cv >= ncv || oy >= to.h || ox0 >= to.w) return;
+    constexpr int IW = (ST - 1) * SW + K;
+    float acc[ST][8];
+#pragma unroll
+    for (int t = 0; t < ST; t++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[t][j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < K; ky++) {
+        float w[K][8];
+#pragma unroll
+        for (int kx = 0; kx < K; kx++) {
+            const float4* wp = reinterpret_cast<const float4*>(sw + (ky * K + kx) * (CBV * 8) + cv * 8);
+            const float4 a = wp[0], b = wp[1];
+            w[kx][0] = a.x; w[kx][1] = a.y; w[kx][2] = a.z; w[kx][3] = a.w;
+            w[kx][4] = b.x; w[kx][5] = b.y; w[kx][6] = b.z; w[kx][7] = b.w;
+        }
+        const __half* rowp = sin + (size_t(oyl * SH + ky) * IWT + st * ST * SW) * (CBV * 8) + cv * 8;
+#pragma unroll
+        for (int i = 0; i < IW; i++) {
+            float x[8];
+            load8h(rowp + size_t(i) * (CBV * 8), x);
+#pragma unroll
+            for (int t = 0; t < ST; t++) {
+                const int kx = i - t * SW;   // compile-time after unrolling
+                if (kx >= 0 && kx < K) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[t][j] = fmaf(x[j], w[kx][j], acc[t][j]);
+                }
+            }
+        }
+    }
+    const int c0 = (cv0 + cv) * 8;
+    float b[8], sc[8], sh[8];
+    {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0)), a1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
+        b[0] = a0.x; b[1] = a0.y; b[2] = a0.z; b[3] = a0.w; b[4] = a1.x; b[5] = a1.y; b[6] = a1.z; b[7] = a1.w;
+    }
+    const bool post = p.ps != nullptr;
+    if (post) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.ps + c0)), s1 = __ldg(reinterpret_cast<const float4*>(p.ps + c0 + 4));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.pt + c0)), t1 = __ldg(reinterpret_cast<const float4*>(p.pt + c0 + 4));
+        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+        sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+    }
+    __half* orow = p.out + (size_t(to.off) + size_t(oy) * to.w) * p.out_cs + c0;
+#pragma unroll
+    for (int t = 0; t < ST; t++) {
+        const int ox = ox0 + t;
+        if (ox >= to.w) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float x = fact<ACT>(acc[t][j] + b[j]);
+            if (post) x = x * sc[j] + sh[j];
+            v[j] = x;
+        }
+        store8h(orow + size_t(ox) * p.out_cs, v);
+    }
+}
+
+template <int K, int SH, int SW, int TH, int CBV>
+static bool dw_tile_launch(const DwDev& d, const ConvArgs& a, int max_h, int max_w, cudaStream_t st) {
+    constexpr int IH = (TH - 1) * SH + K, IWT = 15 * SW + K;
+    const size_t smem = size_t(IH) * IWT * CBV * 16 + size_t(K) * K * CBV * 8 * sizeof(float);
+    const int tiles_x = (max_w + 15) / 16, tiles_y = (max_h + TH - 1) / TH;
+    dim3 grid(tiles_x * tiles_y, a.n_img, (d.cvecs + CBV - 1) / CBV);
+    auto go = [&](auto kern) {
+        static bool configured = false;   // one static per instantiation of this lambda's enclosing template + kernel
+        if (smem > 48 * 1024 && !configured) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            configured = true;
+        }
+        kern<<<grid, TH * 4 * CBV, smem, st>>>(d, tiles_x);
+    };
+    switch (a.epi.act) {
+        case ACT_NONE: go(dwconv_tile_kernel<K, SH, SW, TH, CBV, ACT_NONE>); return true;
+        case ACT_RELU: go(dwconv_tile_kernel<K, SH, SW, TH, CBV, ACT_RELU>); return true;
+        case ACT_HSWISH: go(dwconv_tile_kernel<K, SH, SW, TH, CBV, ACT_HSWISH>); return true;
+        default: return false;
+    }
+}
+
+bool launch_dwconv_tiled(const ConvArgs& a, int max_out_h, int max_out_w, cudaStream_t st) {
+    if (a.epi.res || a.epi.act2 != ACT_NONE || a.out_f32 || a.kh != a.kw) return false;
+    if (2 * a.ph != a.kh - 1 || 2 * a.pw != a.kw - 1) return false;
+    DwDev d{static_cast<const __half*>(a.in), static_cast<__half*>(a.out), a.w, a.epi.bias, a.epi.post_scale, a.epi.post_shift,
+            a.tin, a.tout, a.in_cs, a.out_cs, a.cin_pad / 8, a.cin_pad, a.ph, a.pw};
+    if (!d.bias) return false;
+    const int key = a.kh * 100 + a.sh * 10 + a.sw;
+    // channel block per CTA: 8 vectors (64 channels, 128 B per pixel), 4 for 32-channel layers, 2 for 16/24 channels
+#define VSE_DW_TILE(KK, SHH, SWW, THW, THN)                                                                              \
+    (d.cvecs >= 5   ? dw_tile_launch<KK, SHH, SWW, THW, 8>(d, a, max_out_h, max_out_w, st)                               \
+     : d.cvecs == 4 ? dw_tile_launch<KK, SHH, SWW, THN, 4>(d, a, max_out_h, max_out_w, st)                               \
+                    : dw_tile_launch<KK, SHH, SWW, THN, 2>(d, a, max_out_h, max_out_w, st))
+    switch (key) {
+        case 311: return VSE_DW_TILE(3, 1, 1, 8, 8);
+        case 322: return VSE_DW_TILE(3, 2, 2, 4, 8);
+        case 321: return VSE_DW_TILE(3, 2, 1, 4, 8);
+        case 312: return VSE_DW_TILE(3, 1, 2, 8, 8);
+        case 511: return VSE_DW_TILE(5, 1, 1, 8, 8);
+        case 522: return VSE_DW_TILE(5, 2, 2, 4, 8);
+        case 521: return VSE_DW_TILE(5, 2, 1, 4, 8);
+        case 512: return VSE_DW_TILE(5, 1, 2, 8, 8);
+        default: return false;
+    }
+#undef VSE_DW_TILE
+}
+
+// ------------------------------------------------------------------------------------------------
 // stem: 3x3 stride 2 pad 1, uint8 BGRX -> 16 channels, (x * nscale + nshift) fused into the load
 // ------------------------------------------------------------------------------------------------
 struct StemDev {
