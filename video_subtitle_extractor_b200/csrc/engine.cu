@@ -61,7 +61,7 @@ void Engine::prepare_plan(LoadedPlan& lp) {
     const PlanData& pd = lp.data;
     std::vector<float> host;
     host.reserve(pd.weights.size() * 2 + 4096);
-    struct Off { size_t bias_pk = SIZE_MAX, ps_pk = SIZE_MAX, pb_pk = SIZE_MAX, w = SIZE_MAX, bias = SIZE_MAX, ps = SIZE_MAX, pb = SIZE_MAX, g = SIZE_MAX, b = SIZE_MAX, sc = SIZE_MAX, sh = SIZE_MAX; };
+    struct Off { size_t w_t = SIZE_MAX, bias_pk = SIZE_MAX, ps_pk = SIZE_MAX, pb_pk = SIZE_MAX, w = SIZE_MAX, bias = SIZE_MAX, ps = SIZE_MAX, pb = SIZE_MAX, g = SIZE_MAX, b = SIZE_MAX, sc = SIZE_MAX, sh = SIZE_MAX; };
     std::vector<Off> offs(pd.steps.size());
     lp.dev.assign(pd.steps.size(), StepDev{});
     auto alloc = [&](size_t nfloats) {
@@ -159,6 +159,12 @@ void Engine::prepare_plan(LoadedPlan& lp) {
             case OP_VECLIN: {
                 if (s.wsize[W_WEIGHT] != int64_t(cout) * cin) throw InvalidArg{"veclin weight size mismatch"};
                 o.w = put_vec(pd.w(s, W_WEIGHT), int64_t(cout) * cin, cout * cin);
+                {
+                    o.w_t = alloc(size_t(cout) * cin);
+                    const float* src = pd.w(s, W_WEIGHT);   // [cout][cin]
+                    for (int co = 0; co < cout; co++)
+                        for (int ci = 0; ci < cin; ci++) host[o.w_t + size_t(ci) * cout + co] = src[size_t(co) * cin + ci];
+                }
                 o.bias = put_vec(pd.w(s, W_BIAS), cout, cout);
                 if (s.p[P_HAS_POST]) {
                     o.ps = put_vec(pd.w(s, W_POST_SCALE), cout, cout);
@@ -224,6 +230,7 @@ void Engine::prepare_plan(LoadedPlan& lp) {
         const Off& o = offs[k];
         d.w = ptr(o.w); d.bias = ptr(o.bias); d.post_scale = ptr(o.ps); d.post_shift = ptr(o.pb);
         d.gamma = ptr(o.g); d.beta = ptr(o.b); d.scale = ptr(o.sc); d.shift = ptr(o.sh);
+        d.w_t = ptr(o.w_t);
         d.bias_pk = ptr(o.bias_pk); d.post_scale_pk = ptr(o.ps_pk); d.post_shift_pk = ptr(o.pb_pk);
     }
 }
@@ -549,6 +556,45 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
         const StepDev& d = lp.dev[k];
         const ValueRec& vo = pd.values[s.out];
         const int out_f32 = vo.dtype == DT_F32 && vo.kind == KIND_IMG;
+        // concat gather: a run of CHSCALE / plain nearest-UPSAMPLE steps filling slices of one concat buffer -> one kernel
+        if (prec == 0 && !(cfg.flags & (VSE_FLAG_NO_FAST_KERNELS | VSE_FLAG_NO_CONCAT_GATHER)) && vo.alias_of >= 0 &&
+            (s.op == OP_CHSCALE || (s.op == OP_UPSAMPLE && !s.p[P_HAS_ADD]))) {
+            GatherSrc src[4];
+            int n = 0;
+            size_t j = k;
+            for (; j < pd.steps.size() && n < 4; j++) {
+                const StepRec& sj = pd.steps[j];
+                const ValueRec& vj = pd.values[sj.out];
+                const bool okop = sj.op == OP_CHSCALE || (sj.op == OP_UPSAMPLE && !sj.p[P_HAS_ADD]);
+                if (!okop || vj.alias_of != vo.alias_of || cx.vals[sj.out].geo != cx.vals[s.out].geo || vj.dtype != DT_ACT) break;
+                bool dep = false;   // a later member must not read an earlier member's output
+                for (size_t q = k; q < j; q++) dep = dep || sj.ins[0] == pd.steps[q].out || sj.ins[1] == pd.steps[q].out;
+                if (dep) break;
+                GatherSrc& g = src[n++];
+                g.in = static_cast<const __half*>(ptr_of(sj.ins[0]));
+                g.in_cs = value_cs(pd, sj.ins[0]);
+                g.tin = tab_of(sj.ins[0]);
+                g.scale_px = sj.op == OP_UPSAMPLE ? sj.p[P_SCALE] : 1;
+                g.scale = sj.op == OP_CHSCALE ? static_cast<const float*>(ptr_of(sj.ins[1])) : nullptr;
+                g.scale_c = sj.op == OP_CHSCALE ? pd.values[sj.ins[1]].channels : 0;
+                g.residual = sj.op == OP_CHSCALE ? sj.p[P_RESIDUAL] : 0;
+                g.out = static_cast<__half*>(ptr_of(sj.out));
+                g.out_cs = value_cs(pd, sj.out);
+                g.cvecs = pad8(vj.channels) / 8;
+            }
+            if (n >= 2) {
+                std::sort(src, src + n, [](const GatherSrc& a, const GatherSrc& b) { return a.out < b.out; });
+                launch_concat_gather(src, n, tab_of(s.out), cx.n_img, geo_of(s.out).max_pix, stream);
+                launches++;
+                cx.kind[k] = 2;
+                for (size_t q = k + 1; q < j; q++) {
+                    cx.kind[q] = 3;
+                    if (step_events) cudaEventRecord((*step_events)[q], stream);
+                }
+                k = j - 1;
+                continue;
+            }
+        }
         switch (s.op) {
             case OP_CONV: case OP_STEM: case OP_DWCONV: case OP_DECONV2: {
                 ConvArgs a;
@@ -633,11 +679,12 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                     if (f1.op == OP_VECLIN && f2.op == OP_VECLIN && f1.ins[0] == s.out && f2.ins[0] == f1.out &&
                         pd.values[s.out].last_use == int(k + 1) && pd.values[f1.out].last_use == int(k + 2) && plain(f1) &&
                         plain(f2) && f1.p[P_CIN] == vo.channels && f2.p[P_CIN] == f1.p[P_COUT] && f2.p[P_COUT] == f1.p[P_CIN] &&
-                        lp.dev[k + 1].bias && lp.dev[k + 2].bias && f1.p[P_CIN] + f1.p[P_COUT] <= 8192) {
+                        lp.dev[k + 1].bias && lp.dev[k + 2].bias && lp.dev[k + 1].w_t && lp.dev[k + 2].w_t && f1.p[P_COUT] <= 512 &&
+                        f1.p[P_CIN] + f1.p[P_COUT] <= 8192) {
                         launch_gpool_partial(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), cp, tab_of(s.ins[0]), cx.n_img, partial,
                                              splits, prec, stream);
-                        launch_se_gate(partial, splits, cp, f1.p[P_CIN], f1.p[P_COUT], tab_of(s.ins[0]), lp.dev[k + 1].w,
-                                       lp.dev[k + 1].bias, f1.p[P_ACT], f1.f[F_HS_SLOPE], f1.f[F_HS_OFFSET], lp.dev[k + 2].w,
+                        launch_se_gate(partial, splits, cp, f1.p[P_CIN], f1.p[P_COUT], tab_of(s.ins[0]), lp.dev[k + 1].w_t,
+                                       lp.dev[k + 1].bias, f1.p[P_ACT], f1.f[F_HS_SLOPE], f1.f[F_HS_OFFSET], lp.dev[k + 2].w_t,
                                        lp.dev[k + 2].bias, f2.p[P_ACT], f2.f[F_HS_SLOPE], f2.f[F_HS_OFFSET],
                                        static_cast<float*>(ptr_of(f2.out)), cx.n_img, stream);
                         fused = true;

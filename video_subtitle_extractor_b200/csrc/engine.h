@@ -89,6 +89,7 @@ struct StepDev {
     const float* shift = nullptr;
     const void* w_tc = nullptr;  // half, K-major [cout_pad][k_pad] for the tensor-core path
     // pixel-packed variant of a 1x1 conv (see Engine::load_plan): per-channel constants repeated `pack` times
+    const float* w_t = nullptr;  // VECLIN: transposed (input-major) matrix for the squeeze-excite gate kernel
     const float* bias_pk = nullptr;
     const float* post_scale_pk = nullptr;
     const float* post_shift_pk = nullptr;

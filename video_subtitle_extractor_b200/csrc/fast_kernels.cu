@@ -510,10 +510,13 @@ __device__ __forceinline__ float act_rt(float x, int act, float slope, float off
     }
 }
 
-__global__ void __launch_bounds__(256) se_gate_kernel(SeDev p) {
+// w1t: [c][cm] (input-major), w2t: [cm][c]: consecutive threads own consecutive outputs, so weight reads are coalesced
+// and no warp shuffles sit on the critical path (these matrices are read once per image by a single CTA).
+__global__ void __launch_bounds__(512) se_gate_kernel(SeDev p) {
     extern __shared__ float sm[];
-    float* mean = sm;            // [c]
-    float* hid = sm + p.c;       // [cm]
+    float* mean = sm;                 // [c]
+    float* hid = sm + p.c;            // [cm]
+    float* part = hid + p.cm;         // [blockDim.x]
     const int img = blockIdx.x;
     const float inv = 1.f / float(p.tin[img].h * p.tin[img].w);
     for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
@@ -522,23 +525,31 @@ __global__ void __launch_bounds__(256) se_gate_kernel(SeDev p) {
         mean[c] = s * inv;
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int co = warp; co < p.cm; co += nw) {
-        const float* wr = p.w1 + size_t(co) * p.c;
+    // FC1: cm outputs, K = c split over blockDim / cm thread groups
+    const int groups = max(1, int(blockDim.x) / p.cm);
+    {
+        const int co = threadIdx.x % p.cm, g = threadIdx.x / p.cm;
         float s = 0.f;
-        for (int i = lane; i < p.c; i += 32) s = fmaf(wr[i], mean[i], s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) hid[co] = act_rt(s + p.b1[co], p.act1, p.slope1, p.offset1);
+        if (g < groups) {
+            const int chunk = (p.c + groups - 1) / groups;
+            const int i0 = g * chunk, i1 = min(p.c, i0 + chunk);
+#pragma unroll 4
+            for (int i = i0; i < i1; i++) s = fmaf(p.w1[size_t(i) * p.cm + co], mean[i], s);
+        }
+        part[threadIdx.x] = s;
     }
     __syncthreads();
-    for (int co = warp; co < p.c; co += nw) {
-        const float* wr = p.w2 + size_t(co) * p.cm;
-        float s = 0.f;
-        for (int i = lane; i < p.cm; i += 32) s = fmaf(wr[i], hid[i], s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) p.out[size_t(img) * p.c + co] = act_rt(s + p.b2[co], p.act2, p.slope2, p.offset2);
+    for (int co = threadIdx.x; co < p.cm; co += blockDim.x) {
+        float s = p.b1[co];
+        for (int g = 0; g < groups; g++) s += part[g * p.cm + co];
+        hid[co] = act_rt(s, p.act1, p.slope1, p.offset1);
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < p.c; co += blockDim.x) {
+        float s = p.b2[co];
+#pragma unroll 4
+        for (int i = 0; i < p.cm; i++) s = fmaf(p.w2[size_t(i) * p.c + co], hid[i], s);
+        p.out[size_t(img) * p.c + co] = act_rt(s, p.act2, p.slope2, p.offset2);
     }
 }
 
@@ -546,7 +557,54 @@ void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, 
                     const float* b1, int act1, float slope1, float offset1, const float* w2, const float* b2, int act2,
                     float slope2, float offset2, float* out, int n_img, cudaStream_t st) {
     SeDev d{partial, splits, c_pad, c, cm, tin, w1, b1, w2, b2, act1, act2, slope1, offset1, slope2, offset2, out};
-    se_gate_kernel<<<n_img, 256, size_t(c + cm) * sizeof(float), st>>>(d);
+    const int threads = 512;   // cm <= threads is checked by the caller
+    se_gate_kernel<<<n_img, threads, size_t(c + cm + threads) * sizeof(float), st>>>(d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// concat gather: several CHSCALE / nearest-UPSAMPLE steps that each fill one channel slice of the same concat buffer
+// run as ONE kernel that writes whole pixels (all slices, contiguous 16-byte pieces) — instead of one pass per slice of
+// 48-byte partial-sector writes into a buffer that is larger than L2.
+// ------------------------------------------------------------------------------------------------
+struct GatherDev {
+    GatherSrc s[4];
+    int n, total_cvecs;
+    const ImgTab* tout;
+};
+
+__global__ void __launch_bounds__(256) concat_gather_kernel(GatherDev p) {
+    const int img = blockIdx.y;
+    const ImgTab to = p.tout[img];
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= int64_t(to.h) * to.w * p.total_cvecs) return;
+    int piece = int(idx % p.total_cvecs);
+    const int m = int(idx / p.total_cvecs);
+    const int oy = m / to.w, ox = m - oy * to.w;
+    int k = 0;
+    while (k + 1 < p.n && piece >= p.s[k].cvecs) { piece -= p.s[k].cvecs; k++; }
+    const GatherSrc& g = p.s[k];
+    const ImgTab ti = g.tin[img];
+    const int iy = oy / g.scale_px, ix = ox / g.scale_px;
+    float x[8];
+    load8h(g.in + (size_t(ti.off) + size_t(iy) * ti.w + ix) * g.in_cs + piece * 8, x);
+    if (g.scale) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int c = piece * 8 + j;
+            const float sc = c < g.scale_c ? g.scale[size_t(img) * g.scale_c + c] : 0.f;
+            x[j] = g.residual ? x[j] + x[j] * sc : x[j] * sc;
+        }
+    }
+    store8h(g.out + (size_t(to.off) + m) * g.out_cs + piece * 8, x);
+}
+
+void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_pix, cudaStream_t st) {
+    GatherDev d{};
+    d.n = n;
+    d.tout = tout;
+    for (int i = 0; i < n; i++) { d.s[i] = src[i]; d.total_cvecs += src[i].cvecs; }
+    dim3 grid(cdiv_i(int64_t(max_out_pix) * d.total_cvecs, 256), n_img);
+    concat_gather_kernel<<<grid, 256, 0, st>>>(d);
 }
 
 }  // namespace vse

@@ -1,6 +1,7 @@
 // fast_kernels.h — shape-specialised fp16 kernels (see fast_kernels.cu).  Every launcher returns false when the step
 // does not have the shape it was written for; the engine then uses the generic kernel of nn_kernels.cu.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "nn_kernels.h"
@@ -22,9 +23,19 @@ bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, con
                           float* out, int out_cs, const ImgTab* tin, const ImgTab* tout, int n_img, int max_in_pix,
                           cudaStream_t st);
 
-// squeeze-excite gate from the partial sums written by launch_gpool_partial (nn_kernels): mean -> FC+act -> FC+act
+// squeeze-excite gate from the partial sums written by launch_gpool_partial (nn_kernels): mean -> FC+act -> FC+act.
+// w1 / w2 are the TRANSPOSED (input-major) matrices: w1[c][cm], w2[cm][c]; cm <= 512.
 void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, const ImgTab* tin, const float* w1,
                     const float* b1, int act1, float slope1, float offset1, const float* w2, const float* b2, int act2,
                     float slope2, float offset2, float* out, int n_img, cudaStream_t st);
+
+// one source of a concat gather: a channel slice of the output filled from `in` (nearest-upsampled by scale_px, and/or
+// multiplied by a per-image channel gate as CHSCALE does).  Sources must be ordered by ascending slice offset.
+struct GatherSrc {
+    const __half* in; int in_cs; const ImgTab* tin; int scale_px;
+    const float* scale; int scale_c; int residual;     // optional channel gate (nullptr = plain copy)
+    __half* out; int out_cs; int cvecs;                // slice base pointer, row pitch of the concat buffer, slice width / 8
+};
+void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_pix, cudaStream_t st);
 
 }  // namespace vse
