@@ -668,7 +668,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 const int cp = pad8(pd.values[s.ins[0]].channels);
                 const Geo& g = geo_of(s.ins[0]);
                 // enough CTAs to fill the machine (n_img x splits >= ~2 waves), at least 64 pixels per split
-                int splits = std::max(1, std::min({64, g.max_pix / 64, (2 * sm_count + cx.n_img - 1) / std::max(cx.n_img, 1)}));
+                int splits = std::max(1, std::min({64, g.max_pix / 64, std::max((4 * sm_count + cx.n_img - 1) / std::max(cx.n_img, 1), g.max_pix / 1024)}));
                 float* partial = reinterpret_cast<float*>(static_cast<char*>(arena_[which].p) + cx.scratch_off);
                 // squeeze-excite: GPOOL -> VECLIN -> VECLIN (each the sole consumer of the previous) -> one gate kernel
                 bool fused = false;
@@ -755,8 +755,14 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 // copy ins[0] into channels [coff, coff+c) of the concat root `out`
                 const int coff = s.p[P_SCALE], c = s.p[P_COUT];
                 char* dst = static_cast<char*>(ptr_of(s.out)) + size_t(coff) * elt_size(vo);
-                launch_copy(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), dst, value_cs(pd, s.out), pad8(c), geo_of(s.ins[0]).total, prec,
-                            stream);
+                if (coff % 8 == 0) {
+                    launch_copy(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), dst, value_cs(pd, s.out), pad8(c), geo_of(s.ins[0]).total,
+                                prec, stream);
+                } else {
+                    const int fill = std::min(pad8(coff + c), value_cs(pd, s.out)) - coff;   // zero the pad channels behind the slice
+                    launch_copy_unaligned(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), dst, value_cs(pd, s.out), c, fill,
+                                          geo_of(s.ins[0]).total, prec, stream);
+                }
                 launches++;
                 break;
             }

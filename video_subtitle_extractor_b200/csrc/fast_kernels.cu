@@ -298,7 +298,8 @@ bool launch_dwconv_tiled(const ConvArgs& a, int max_out_h, int max_out_w, cudaSt
     const int key = a.kh * 100 + a.sh * 10 + a.sw;
     // channel block per CTA: 8 vectors (64 channels, 128 B per pixel), 4 for 32-channel layers, 2 for 16/24 channels
 #define VSE_DW_TILE(KK, SHH, SWW, THW, THN)                                                                              \
-    (d.cvecs >= 5   ? dw_tile_launch<KK, SHH, SWW, THW, 8>(d, a, max_out_h, max_out_w, st)                               \
+    (d.cvecs >= 5   ? (max_out_h <= 4 ? dw_tile_launch<KK, SHH, SWW, 4, 8>(d, a, max_out_h, max_out_w, st)               \
+                                      : dw_tile_launch<KK, SHH, SWW, THW, 8>(d, a, max_out_h, max_out_w, st))            \
      : d.cvecs == 4 ? dw_tile_launch<KK, SHH, SWW, THN, 4>(d, a, max_out_h, max_out_w, st)                               \
                     : dw_tile_launch<KK, SHH, SWW, THN, 2>(d, a, max_out_h, max_out_w, st))
     switch (key) {
@@ -422,7 +423,7 @@ struct HeadDev {
 };
 
 template <int C>
-__global__ void __launch_bounds__(128) db_head_fused_kernel(HeadDev p) {
+__global__ void __launch_bounds__(128, 4) db_head_fused_kernel(HeadDev p) {
     __shared__ __align__(16) float sw1[4 * C * C];
     __shared__ __align__(16) float sw2[4 * C];
     __shared__ float sb1[C];

@@ -372,12 +372,29 @@ __global__ void __launch_bounds__(256) gpool_partial_kernel(const T* in, int in_
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = 0.f;
         if (pl < nl) {
-            for (int pidx = p0 + pl; pidx < p1; pidx += nl) {
+            // four independent loads in flight per thread (the sum order per thread stays fixed: deterministic)
+            float acc1[8], acc2[8], acc3[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc1[j] = acc2[j] = acc3[j] = 0.f;
+            const T* base = in + size_t(ti.off) * in_cs + (cvb + cv) * 8;
+            int pidx = p0 + pl;
+            for (; pidx + 3 * nl < p1; pidx += 4 * nl) {
+                float x0[8], x1[8], x2[8], x3[8];
+                V8<T>::load(base + size_t(pidx) * in_cs, x0);
+                V8<T>::load(base + size_t(pidx + nl) * in_cs, x1);
+                V8<T>::load(base + size_t(pidx + 2 * nl) * in_cs, x2);
+                V8<T>::load(base + size_t(pidx + 3 * nl) * in_cs, x3);
+#pragma unroll
+                for (int j = 0; j < 8; j++) { acc[j] += x0[j]; acc1[j] += x1[j]; acc2[j] += x2[j]; acc3[j] += x3[j]; }
+            }
+            for (; pidx < p1; pidx += nl) {
                 float x[8];
-                V8<T>::load(in + (size_t(ti.off) + pidx) * in_cs + (cvb + cv) * 8, x);
+                V8<T>::load(base + size_t(pidx) * in_cs, x);
 #pragma unroll
                 for (int j = 0; j < 8; j++) acc[j] += x[j];
             }
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = (acc[j] + acc1[j]) + (acc2[j] + acc3[j]);
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) red[threadIdx.x][j] = acc[j];
@@ -641,6 +658,26 @@ __global__ void __launch_bounds__(256) copy_kernel(const T* in, int in_cs, T* ou
     float x[8];
     V8<T>::load(in + pix * in_cs + cv * 8, x);
     V8<T>::store(out + pix * out_cs + cv * 8, x);
+}
+
+// concat slice at a channel offset that is not a multiple of 8 (e.g. the 1 + 64 channel concat of PFHeadLocal in
+// reference backend/models/V4/ch_det): scalar copy of `c` channels, then zeros up to the next multiple of 8 so that the
+// consumer's padded channels hold finite values
+template <typename T>
+__global__ void __launch_bounds__(256) copy_unaligned_kernel(const T* in, int in_cs, T* out, int out_cs, int c, int c_fill,
+                                                            int64_t pixels) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= pixels * c_fill) return;
+    const int ch = int(idx % c_fill);
+    const size_t pix = size_t(idx / c_fill);
+    out[pix * out_cs + ch] = ch < c ? in[pix * in_cs + ch] : from_f<T>(0.f);
+}
+
+void launch_copy_unaligned(const void* in, int in_cs, void* out, int out_cs, int c, int c_fill, int64_t pixels, int prec,
+                           cudaStream_t st) {
+    int grid = cdiv(pixels * c_fill, 256);
+    if (prec == 0) copy_unaligned_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, (__half*)out, out_cs, c, c_fill, pixels);
+    else copy_unaligned_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, (float*)out, out_cs, c, c_fill, pixels);
 }
 
 void launch_copy(const void* in, int in_cs, void* out, int out_cs, int c_pad, int64_t pixels, int prec, cudaStream_t st) {

@@ -68,6 +68,9 @@ void launch_eltwise(const void* in, int in_cs, void* out, int out_cs, int c_pad,
                     const float* scale, const float* shift, int act, float hs_slope, float hs_offset, int out_f32,
                     int prec, cudaStream_t st);
 void launch_copy(const void* in, int in_cs, void* out, int out_cs, int c_pad, int64_t pixels, int prec, cudaStream_t st);
+// `out` already points at the (unaligned) first channel of the slice; writes c channels + zeros up to c_fill
+void launch_copy_unaligned(const void* in, int in_cs, void* out, int out_cs, int c, int c_fill, int64_t pixels, int prec,
+                           cudaStream_t st);
 void launch_layernorm(const void* in, int in_cs, void* out, int out_cs, int c, int64_t pixels, const float* gamma,
                       const float* beta, float eps, int prec, cudaStream_t st);
 void launch_attention(const void* qkv, int qkv_cs, void* out, int out_cs, int heads, int dim, float qscale,

@@ -191,13 +191,28 @@ static void stage_frames(const uint8_t* const* frames, const int32_t* h, const s
     size_t total = 0;
     for (int i = 0; i < n; i++) total += (size_t(h[i]) * fstride[i] + 255) & ~size_t(255);
     buf.reserve(total);
-    size_t off = 0;
+    // frames that follow each other in host memory (a decoded batch in one pinned block) go up in ONE copy: a 1080p batch
+    // of 32 is 32 driver calls otherwise, ~0.5 ms of host time per step
+    size_t off = 0, run_off = 0, run_bytes = 0;
+    const uint8_t* run_src = nullptr;
+    auto flush = [&]() {
+        if (run_bytes) VSE_CUDA(cudaMemcpyAsync(buf.as<uint8_t>() + run_off, run_src, run_bytes, cudaMemcpyHostToDevice, st));
+        run_bytes = 0;
+    };
     for (int i = 0; i < n; i++) {
         const size_t bytes = size_t(h[i]) * fstride[i];
-        VSE_CUDA(cudaMemcpyAsync(buf.as<uint8_t>() + off, frames[i], bytes, cudaMemcpyHostToDevice, st));
+        if (run_bytes && frames[i] == run_src + run_bytes && off == run_off + run_bytes) {
+            run_bytes += bytes;
+        } else {
+            flush();
+            run_src = frames[i];
+            run_off = off;
+            run_bytes = bytes;
+        }
         fdev[i] = buf.as<uint8_t>() + off;
         off += (bytes + 255) & ~size_t(255);
     }
+    flush();
 }
 
 // vse_prefetch: start the host->device copy of the NEXT batch on the copy stream while the current vse_run computes.
