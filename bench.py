@@ -365,7 +365,8 @@ def run_b200(args, rank, local_rank, world):
                        "precision": "fp16 activations, fp32 accumulate"},
             "device_ms_per_step": dev_s / args.steps * 1e3, "stage_ms_last_e2e_step": stage_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": wall_e2e_max / args.steps * 1e3},
+                    "ms_per_step": wall_e2e_max / args.steps * 1e3, "device_ms_per_step": dev_s_e2e / args.steps * 1e3,
+                    "overlap": "vse_prefetch: the copy of step k+1 is issued before step k runs (copy stream)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
     eng.close()
