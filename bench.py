@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--pool", type=int, default=3, help="distinct batches cycled through (3 x 32 x 6.2 MB > L2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="vse_config.flags (VSE_FLAG_* A/B switches, profiling only)")
     return ap.parse_args()
 
 
@@ -271,7 +272,7 @@ def run_b200(args, rank, local_rank, world):
         dev_batches.append(pinned.to(dev))
     torch.cuda.synchronize()
 
-    eng = E.Engine(device=local_rank, precision=E.PRECISION_FP16)
+    eng = E.Engine(device=local_rank, precision=E.PRECISION_FP16, flags=args.flags)
     eng.load_plan(E.PLAN_DET, det_blob, DET)
     eng.load_plan(E.PLAN_REC, rec_blob, REC)
     hs, ws = [H] * B, [W] * B

@@ -51,7 +51,7 @@ enum {
     /* finer A/B switches (bisecting numerical differences); each disables one specialised path */
     VSE_FLAG_NO_FUSED_HEAD = 4, VSE_FLAG_NO_SE_FUSION = 8, VSE_FLAG_NO_ROWBOX = 16, VSE_FLAG_NO_FAST_DW = 32,
     VSE_FLAG_NO_FAST_STEM = 64, VSE_FLAG_NO_PIXEL_PACK = 128,
-    VSE_FLAG_NO_CONCAT_GATHER = 256
+    VSE_FLAG_NO_CONCAT_GATHER = 256, VSE_FLAG_NO_HALO = 512
 };
 
 /* Mirrors the knobs the reference passes to PaddleOCR / TextDetector (ocr.py:91-113) and the

@@ -475,7 +475,8 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         }
         const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_off[k];
         std::string why = tc_conv_setup(cx.tc[k], vptr(which, s.ins[0]), value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], flat,
-                                        gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX));
+                                        gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX),
+                                        !(cfg.flags & VSE_FLAG_NO_HALO));
         if (!why.empty()) cx.tc[k].valid = false;
     }
 }

@@ -37,7 +37,7 @@ static constexpr int kMaxSmem = 227 * 1024;
 
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
-        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total;
+        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx;
     void* out;
     int out_cs;
     const float* bias;
@@ -175,6 +175,20 @@ __device__ __forceinline__ void umma_f16_words(uint32_t d_tmem, uint32_t a_lo, u
         "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_words2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 da, {%1, %6};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(a_hi)
+        : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -300,9 +314,9 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
             const int per_img = p.tiles_x * p.tiles_y;
             img = m_tile / per_img;
             const int r = m_tile - img * per_img;
-            y0 = (r / p.tiles_x) * 8;
-            x0 = (r % p.tiles_x) * 16;
-            const int y = y0 + (row >> 4), x = x0 + (row & 15);
+            y0 = (r / p.tiles_x) * (p.halo ? 16 : 8);
+            x0 = (r % p.tiles_x) * (p.halo ? 8 : 16);
+            const int y = y0 + (p.halo ? row >> 3 : row >> 4), x = x0 + (p.halo ? row & 7 : row & 15);
             if (y < p.H && x < p.W) pix = (long long)img * p.H * p.W + (long long)y * p.W + x;
         } else {
             const long long m = (long long)m_tile * BLOCK_M + row;
@@ -370,6 +384,89 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUten
 }
 
 // ------------------------------------------------------------------------------------------------
+// MMA issuer warp.  The whole warp walks the loop (warp-uniform control flow and addresses, so the descriptor arithmetic
+// stays on the uniform datapath); one elected lane issues the tcgen05 instructions.  With N as small as 32 an MMA occupies
+// the tensor pipe for ~16 cycles, so the scalar instructions spent per k-iteration here bound the kernel: the loop is
+// instantiated per addressing mode (MODE 0: one operand tile per k-iteration; 1: row box, KH vertical taps per tile;
+// 2: halo box, KH x KW taps per tile) with the common 3x3 shapes unrolled (KH / KW = 0: run-time extents), and every
+// per-iteration quantity is a running sum instead of a product.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int KH_, int KW_>
+__device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full, uint64_t* empty, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, uint32_t tmem_base, uint32_t a_lo0, uint32_t bres_lo,
+                                              uint32_t stage16, int k_iters) {
+    const int KH = KH_ ? KH_ : p.kh, KW = KW_ ? KW_ : p.kw;
+    const uint32_t idesc = (1u << 4) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+    const int total_tiles = p.num_m_tiles * p.n_chunks;
+    const int stages = p.stages, acc_stages = p.acc_stages, num_kb = p.num_kb, n_chunk = p.n_chunk;
+    const bool resident = p.b_resident != 0;
+    const uint32_t b_step = uint32_t(n_chunk * 8);                  // one [n_chunk x 64] weight slice in 16-byte units
+    const uint32_t a16 = uint32_t(p.a_bytes >> 4);
+    const int ks_last = min(BLOCK_K / UMMA_K, (p.cin - (num_kb - 1) * BLOCK_K + UMMA_K - 1) / UMMA_K);   // all-zero K tail skipped
+    // strides between the weight slices of consecutive taps
+    const uint32_t b_ky_step = resident ? uint32_t(KW * num_kb) * b_step : b_step;     // MODE 1
+    const uint32_t b_tap_step = resident ? uint32_t(num_kb) * b_step : b_step;         // MODE 2
+    const uint32_t bw = uint32_t(8 + KW - 1);                                          // MODE 2: box width in pixels
+    // MODE 2: SBO = one image row of the box.  The base-offset field stays 0: measured on B200, the 128B-swizzle XOR is
+    // taken from the absolute shared-memory address bits (as TMA writes them), so a start address that is not 1024-byte
+    // aligned needs no phase correction (setting the field breaks parity).
+    const uint32_t halo_hi = uint32_t((bw * 128) >> 4) | (1u << 14) | (2u << 29);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0, a_lo = a_lo0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * n_chunk);
+        int kb = 0;
+        uint32_t b_it = bres_lo;                                     // resident slice of (k-iteration `it`)
+        for (int it = 0; it < k_iters; it++) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const int ks = (kb == num_kb - 1) ? ks_last : BLOCK_K / UMMA_K;
+            const uint32_t b_first = resident ? b_it : a_lo + a16;
+            if (elect_one()) {
+                if constexpr (MODE == 0) {
+                    umma_f16_words(d_tmem, a_lo, b_first, idesc, it != 0 ? 1u : 0u);
+                    if (ks > 1) umma_f16_words(d_tmem, a_lo + 2, b_first + 2, idesc, 1u);
+                    if (ks > 2) umma_f16_words(d_tmem, a_lo + 4, b_first + 4, idesc, 1u);
+                    if (ks > 3) umma_f16_words(d_tmem, a_lo + 6, b_first + 6, idesc, 1u);
+                } else if constexpr (MODE == 1) {
+#pragma unroll
+                    for (int ky = 0; ky < KH; ky++) {
+                        const uint32_t a_t = a_lo + uint32_t(ky * 128);           // next image row of the box: 16 px * 128 B
+                        const uint32_t b_t = b_first + uint32_t(ky) * b_ky_step;
+                        umma_f16_words(d_tmem, a_t, b_t, idesc, (it | ky) != 0 ? 1u : 0u);
+                        if (ks > 1) umma_f16_words(d_tmem, a_t + 2, b_t + 2, idesc, 1u);
+                        if (ks > 2) umma_f16_words(d_tmem, a_t + 4, b_t + 4, idesc, 1u);
+                        if (ks > 3) umma_f16_words(d_tmem, a_t + 6, b_t + 6, idesc, 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int ky = 0; ky < KH; ky++)
+#pragma unroll
+                        for (int kx = 0; kx < KW; kx++) {
+                            const uint32_t a_t = a_lo + (uint32_t(ky) * bw + uint32_t(kx)) * 8u;   // pixel rows of 128 B
+                            const uint32_t b_t = b_first + uint32_t(ky * KW + kx) * b_tap_step;
+                            umma_f16_words2(d_tmem, a_t, halo_hi, b_t, idesc, (it | ky | kx) != 0 ? 1u : 0u);
+                            if (ks > 1) umma_f16_words2(d_tmem, a_t + 2, halo_hi, b_t + 2, idesc, 1u);
+                            if (ks > 2) umma_f16_words2(d_tmem, a_t + 4, halo_hi, b_t + 4, idesc, 1u);
+                            if (ks > 3) umma_f16_words2(d_tmem, a_t + 6, halo_hi, b_t + 6, idesc, 1u);
+                        }
+                }
+                umma_commit(&empty[stage]);                            // smem slot is free once these MMAs have read it
+                if (it == k_iters - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+            }
+            __syncwarp();
+            b_it += b_step;
+            if (++kb == num_kb) kb = 0;
+            a_lo += stage16;
+            if (++stage == stages) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+        }
+        if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
@@ -378,7 +475,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // rowbox (KxK): one A box of 8 + kh - 1 image rows per (kx, k-block) serves all kh vertical taps; B holds their kh slices
-    const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.rowbox ? p.kh : 1);
+    // halo (KxK, kernels up to 5x5): ONE box of (16 + kh - 1) x (8 + kw - 1) pixels per k-block serves every tap — the MMA
+    // descriptors of tap (ky, kx) start (ky * box_w + kx) pixel rows into the box (tile = 16 rows x 8 columns, so that the
+    // 8-row groups of the operand are one image row each, a uniform stride apart)
+    const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.halo ? p.kh * p.kw : p.rowbox ? p.kh : 1);
     const int stage_bytes = p.a_bytes + b_bytes;
     uint8_t* bres = smem + size_t(p.stages) * stage_bytes;          // resident weights: [tap][k-block][n_chunk x 64]
     uint8_t* sout = bres + p.b_total;                               // kOutBufs staging tiles for the TMA stores
@@ -426,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int total_tiles = p.num_m_tiles * p.n_chunks;
     const int taps = p.kh * p.kw;
-    const int k_iters = (p.rowbox ? p.kw : taps) * p.num_kb;
+    const int k_iters = (p.halo ? 1 : p.rowbox ? p.kw : taps) * p.num_kb;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -446,15 +546,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int per_img = p.tiles_x * p.tiles_y;
                     img = m_tile / per_img;
                     const int r = m_tile - img * per_img;
-                    y0 = (r / p.tiles_x) * 8;
-                    x0 = (r % p.tiles_x) * 16;
+                    y0 = (r / p.tiles_x) * (p.halo ? 16 : 8);
+                    x0 = (r % p.tiles_x) * (p.halo ? 8 : 16);
                 }
                 for (int it = 0; it < k_iters; it++) {
                     const int tap = it / p.num_kb, kb = it - tap * p.num_kb;   // rowbox: tap = kx
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], uint32_t(stage_bytes));
+                    mbar_expect_tx(&full[stage], uint32_t(p.a_tx + b_bytes));
                     uint8_t* a_dst = smem + size_t(stage) * stage_bytes;
-                    if (p.rowbox) {
+                    if (p.halo) {
+                        tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 - p.pw, y0 - p.ph, img);
+                        for (int tp = 0; tp < taps && !p.b_resident; tp++)
+                            tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * BLOCK_K,
+                                        n_idx * p.n_chunk);
+                    } else if (p.rowbox) {
                         tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 + tap - p.pw, y0 - p.ph, img);
                         for (int ky = 0; ky < p.kh && !p.b_resident; ky++)
                             tma_load_2d(a_dst + p.a_bytes + ky * p.n_chunk * 128, &map_b, &full[stage],
@@ -474,53 +579,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        // The whole warp walks the loop (warp-uniform control flow and addresses, so the descriptor arithmetic stays on the
-        // uniform datapath); one elected lane issues the tcgen05 instructions.  With N as small as 32 an MMA costs ~16
-        // tensor-pipe cycles, so every scalar instruction spent per MMA in this loop shows up in the kernel time.
-        const uint32_t idesc = (1u << 4) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        // ---------------- MMA issuer (see mma_warp_loop) ----------------
         if (p.b_resident) {
             mbar_wait(b_full, 0);
             tc_fence_after();
         }
-        const uint32_t smem_base = smem_u32(smem);
-        const uint32_t bres_lo = umma_desc_lo(smem_u32(bres));
-        const uint32_t b_step = uint32_t(p.n_chunk * 8);                 // one [n_chunk x 64] weight slice, in 16-byte units
-        const int nky = p.rowbox ? p.kh : 1;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + uint32_t(acc * p.n_chunk);
-            int kb = 0, tap_it = 0;
-            for (int it = 0; it < k_iters; it++) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint32_t a_lo = umma_desc_lo(smem_base + uint32_t(stage * stage_bytes));
-                const int ksteps = min(BLOCK_K / UMMA_K, (p.cin - kb * BLOCK_K + UMMA_K - 1) / UMMA_K);   // skip all-zero K tail
-                if (elect_one()) {
-                    for (int ky = 0; ky < nky; ky++) {
-                        const uint32_t a_ky = a_lo + uint32_t(ky * 128);   // next image row of the box: 16 px * 128 B
-                        const uint32_t b_ky = p.b_resident
-                            ? bres_lo + uint32_t((p.rowbox ? ky * p.kw + tap_it : tap_it) * p.num_kb + kb) * b_step
-                            : a_lo + uint32_t(p.a_bytes >> 4) + uint32_t(ky) * b_step;
-                        const uint32_t first = (it | ky) != 0 ? 1u : 0u;
-                        umma_f16_words(d_tmem, a_ky, b_ky, idesc, first);
-                        if (ksteps > 1) umma_f16_words(d_tmem, a_ky + 2, b_ky + 2, idesc, 1u);
-                        if (ksteps > 2) umma_f16_words(d_tmem, a_ky + 4, b_ky + 4, idesc, 1u);
-                        if (ksteps > 3) umma_f16_words(d_tmem, a_ky + 6, b_ky + 6, idesc, 1u);
-                    }
-                    umma_commit(&empty[stage]);                            // smem slot is free once these MMAs have read it
-                    if (it == k_iters - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
-                }
-                __syncwarp();
-                if (++kb == p.num_kb) { kb = 0; tap_it++; }
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            }
-            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+        const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem)), bres_lo = umma_desc_lo(smem_u32(bres));
+        const uint32_t stage16 = uint32_t(stage_bytes >> 4);
+        if (p.halo) {
+            if (p.kh == 3 && p.kw == 3) mma_warp_loop<2, 3, 3>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
+            else mma_warp_loop<2, 0, 0>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
+        } else if (p.rowbox) {
+            if (p.kh == 3) mma_warp_loop<1, 3, 0>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
+            else mma_warp_loop<1, 0, 0>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
+        } else {
+            mma_warp_loop<0, 1, 1>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
         }
     } else {
         // ---------------- epilogue: warps 2..9 ----------------
@@ -621,7 +694,7 @@ static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t
 }
 
 std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
-                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox) {
+                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox, bool allow_halo) {
     t.valid = false;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (in_cs & 7)) return "activation view not 16-byte aligned";
     if (pixels <= 0) return "empty";
@@ -629,6 +702,7 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
     t.k_pad = w.k_pad;
     t.cin = cin;
     t.rowbox = 0;
+    t.halo = 0;
     t.num_kb = (cin + BLOCK_K - 1) / BLOCK_K;
     t.n_chunk = w.n_chunk;
     t.n_chunks = w.n_chunks;
@@ -647,8 +721,13 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
     } else {
         t.spatial = 1;
         t.n_img = n_img; t.H = H; t.W = W;
-        t.tiles_x = (W + 15) / 16;
-        t.tiles_y = (H + 7) / 8;
+        // halo tiles (16 rows x 8 columns) for kernels up to 5x5: needs >= 3 stages of one box (+ the taps' weight slices)
+        const int h_box = (16 + kh - 1) * (8 + kw - 1) * 128;
+        const int h_stage = round_up_i(h_box, 1024) + (t.b_resident ? 0 : kh * kw * w.n_chunk * 128);
+        t.halo = (allow_halo && kh > 1 && kh <= 5 && kw <= 5 && kw > 1 &&
+                  3 * h_stage + (t.b_resident ? b_all : 0) <= kMaxSmem - 16384 - kOutBufs * kOutBufBytes) ? 1 : 0;
+        t.tiles_x = t.halo ? (W + 7) / 8 : (W + 15) / 16;
+        t.tiles_y = t.halo ? (H + 15) / 16 : (H + 7) / 8;
         t.num_m_tiles = n_img * t.tiles_x * t.tiles_y;
         cuuint64_t dims[4] = {cuuint64_t(cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(n_img)};
         cuuint64_t strides[3] = {cuuint64_t(in_cs) * 2, cuuint64_t(W) * in_cs * 2, cuuint64_t(H) * W * in_cs * 2};
@@ -656,8 +735,8 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         // traffic for the activations.  Needs >= 3 pipeline stages of (box + kh weight slices) in shared memory.
         const int a_box = (8 + kh - 1) * 16 * 128;
         const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + kh * w.n_chunk * 128);
-        t.rowbox = (allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - 16384 - kOutBufs * kOutBufBytes) ? 1 : 0;
-        cuuint32_t box[4] = {BLOCK_K, 16, cuuint32_t(t.rowbox ? 8 + kh - 1 : 8), 1};
+        t.rowbox = (!t.halo && allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - 16384 - kOutBufs * kOutBufBytes) ? 1 : 0;
+        cuuint32_t box[4] = {BLOCK_K, cuuint32_t(t.halo ? 8 + kw - 1 : 16), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + kh - 1 : 8), 1};
         err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box);
     }
     if (!err.empty()) return err;
@@ -679,7 +758,7 @@ static std::string tc_output_map(TcConv& t) {
     if (t.spatial) {
         cuuint64_t dims[4] = {cuuint64_t(t.n_store), cuuint64_t(t.W), cuuint64_t(t.H), cuuint64_t(t.n_img)};
         cuuint64_t strides[3] = {cuuint64_t(t.out_cs) * 2, cuuint64_t(t.W) * t.out_cs * 2, cuuint64_t(t.H) * t.W * t.out_cs * 2};
-        cuuint32_t box[4] = {BLOCK_K, 16, 8, 1};
+        cuuint32_t box[4] = {BLOCK_K, cuuint32_t(t.halo ? 8 : 16), cuuint32_t(t.halo ? 16 : 8), 1};
         err = encode(&t.map_o, t.out, 4, dims, strides, box);
     } else {
         cuuint64_t dims[2] = {cuuint64_t(t.n_store), cuuint64_t(t.M)};
@@ -703,13 +782,15 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = t.num_m_tiles;
     p.cin = t.cin;
     p.rowbox = t.rowbox;
-    p.a_bytes = t.rowbox ? (8 + t.kh - 1) * 16 * 128 : A_BYTES;
+    p.halo = t.halo;
+    p.a_tx = t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh - 1) * 16 * 128 : A_BYTES;
+    p.a_bytes = round_up_i(p.a_tx, 1024);
     p.n_total = t.n_chunk * t.n_chunks;
     p.param_smem = p.n_total <= kParamSmemMaxCh ? 1 : 0;
     const int param_bytes = p.param_smem ? 3 * p.n_total * int(sizeof(float)) : 0;
     p.b_resident = t.b_resident;
     p.b_total = t.b_resident ? t.kh * t.kw * t.num_kb * t.n_chunk * 128 : 0;
-    const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.rowbox ? t.kh : 1));
+    const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.halo ? t.kh * t.kw : t.rowbox ? t.kh : 1));
     const int budget = kMaxSmem - 1024 - kBarRegion - param_bytes - p.b_total - kOutBufs * kOutBufBytes;
     p.stages = std::max(2, std::min(8, budget / stage_bytes));
     // TMEM accumulator ring: the MMA warp runs up to acc_stages tiles ahead of the epilogue (hides the commit -> wait ->

@@ -43,6 +43,7 @@ struct TcConv {
     int rowbox = 0;         // KxK: A boxes span 8 + kh - 1 image rows and serve all vertical taps (see gemm_tc.cu)
     int pack = 0;           // >0: pixel-packed flat conv (rows of `pack` pixels)
     int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
+    int halo = 0;           // KxK: one (16 + kh - 1) x (8 + kw - 1) box per k-block serves every tap (see gemm_tc.cu)
     int num_kb = 1;         // 64-channel K blocks per tap
     int k_pad = 64;
     int n_chunk = 16, n_chunks = 1, n_store = 8;
@@ -56,7 +57,8 @@ struct TcConv {
 // Fills map_a/map_b + tile counts. `in`: activation base (fp16, channel stride in_cs), `wdev`: packed weights on device.
 // Returns an empty string on success, else the reason the step cannot use the tensor-core path.
 std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
-                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox = true);
+                          int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox = true,
+                          bool allow_halo = true);
 
 // returns an empty string on success, else why the launch was not possible (nothing launched)
 std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st);
