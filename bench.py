@@ -47,8 +47,18 @@ def parse_args():
     ap.add_argument("--pool", type=int, default=3, help="distinct batches cycled through (3 x 32 x 6.2 MB > L2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--det", default=None, help="detector model (default V4/ch_det_fast = BASELINE configs[1]); needs its packed plan")
+    ap.add_argument("--rec", default=None, help="recogniser model (default V4/en_rec_fast)")
     ap.add_argument("--flags", type=int, default=0, help="vse_config.flags (VSE_FLAG_* A/B switches, profiling only)")
     return ap.parse_args()
+
+
+def apply_model_args(args):
+    global DET, REC
+    if args.det:
+        DET = args.det
+    if args.rec:
+        REC = args.rec
 
 
 def env_rank():
@@ -380,6 +390,7 @@ def run_b200(args, rank, local_rank, world):
 
 def main():
     args = parse_args()
+    apply_model_args(args)
     rank, local_rank, world = env_rank()
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -12,6 +12,8 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "plan.h"
 
 namespace vse {
@@ -296,9 +298,10 @@ bool launch_dwconv_tiled(const ConvArgs& a, int max_out_h, int max_out_w, cudaSt
             a.tin, a.tout, a.in_cs, a.out_cs, a.cin_pad / 8, a.cin_pad, a.ph, a.pw};
     if (!d.bias) return false;
     const int key = a.kh * 100 + a.sh * 10 + a.sw;
+    static const bool dw_th4 = [] { const char* e = getenv("VSE_DW_TH4"); return e && atoi(e) != 0; }();   // tuning knob
     // channel block per CTA: 8 vectors (64 channels, 128 B per pixel), 4 for 32-channel layers, 2 for 16/24 channels
 #define VSE_DW_TILE(KK, SHH, SWW, THW, THN)                                                                              \
-    (d.cvecs >= 5   ? (max_out_h <= 4 ? dw_tile_launch<KK, SHH, SWW, 4, 8>(d, a, max_out_h, max_out_w, st)               \
+    (d.cvecs >= 5   ? ((max_out_h <= 4 || dw_th4) ? dw_tile_launch<KK, SHH, SWW, 4, 8>(d, a, max_out_h, max_out_w, st)               \
                                       : dw_tile_launch<KK, SHH, SWW, THW, 8>(d, a, max_out_h, max_out_w, st))            \
      : d.cvecs == 4 ? dw_tile_launch<KK, SHH, SWW, THN, 4>(d, a, max_out_h, max_out_w, st)                               \
                     : dw_tile_launch<KK, SHH, SWW, THN, 2>(d, a, max_out_h, max_out_w, st))

@@ -52,7 +52,7 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 // block (32, 8): a warp covers 32 consecutive pixels of one row; the initial label is the start of the pixel's
 // run inside that 32-pixel segment (one ballot, no chains along rows)
 __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ prob, const DetFrame* __restrict__ frames,
-                                                     float thresh, int* __restrict__ labels) {
+                                                     float thresh, int* __restrict__ labels, int* __restrict__ status) {
     const DetFrame fr = frames[blockIdx.z];
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const bool in = x < fr.rw && y < fr.rh;
@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ p
     bool fg = false;
     if (in) {
         g = fr.map_off + y * fr.rw + x;
-        fg = prob[g] > thresh;
+        const float pv = prob[g];
+        fg = pv > thresh;
+        // a probability is a sigmoid output: anything non-finite means the network overflowed its activation type
+        if (!(fabsf(pv) <= 1.5f)) atomicOr(&status[blockIdx.z], 4);
     }
     const unsigned mask = __ballot_sync(0xffffffffu, fg);
     if (!in) return;
@@ -320,7 +323,7 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
     cudaMemsetAsync(ws.n_comp, 0, sizeof(int) * n_frames, st);
     cudaMemsetAsync(ws.status, 0, sizeof(int) * n_frames, st);
     dim3 blk(32, 8), grid((max_rw + 31) / 32, (max_rh + 7) / 8, n_frames);
-    db_label_init<<<grid, blk, 0, st>>>(prob, frames_dev, p.thresh, ws.labels);
+    db_label_init<<<grid, blk, 0, st>>>(prob, frames_dev, p.thresh, ws.labels, ws.status);
     db_label_merge<<<grid, blk, 0, st>>>(frames_dev, ws.labels);
     db_label_flatten<<<grid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox);
     db_bbox<<<grid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.bbox);

@@ -158,13 +158,16 @@ class Engine:
         n = len(frames)
         cap = max(1, n * int(self.cfg.max_boxes_per_frame))
         T = self.max_text_len
-        n_boxes = np.zeros(max(n, 1), np.int32)
-        quads = np.zeros((cap, 4, 2), np.float32)
-        det_score = np.zeros(cap, np.float32)
-        ids = np.zeros((cap, T), np.int32)
-        id_len = np.zeros(cap, np.int32)
-        rec_score = np.zeros(cap, np.float32)
-        rec_width = np.zeros(cap, np.int32)
+        # result buffers are caller-owned (C-ABI contract); keep one set per engine and batch size instead of allocating
+        # and zero-filling ~2 MB per call — the engine writes every field it reports a count for
+        key = (n, cap, T)
+        if getattr(self, "_res_key", None) != key:
+            self._res_key = key
+            self._res_buf = (np.zeros(max(n, 1), np.int32), np.zeros((cap, 4, 2), np.float32), np.zeros(cap, np.float32),
+                             np.zeros((cap, T), np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32),
+                             np.zeros(cap, np.int32))
+        n_boxes, quads, det_score, ids, id_len, rec_score, rec_width = self._res_buf
+        n_boxes[:] = 0
         res = VseResult()
         res.box_capacity, res.max_text_len = cap, T
         as_p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
