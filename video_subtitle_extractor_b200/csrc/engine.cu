@@ -576,6 +576,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 g.in_cs = value_cs(pd, sj.ins[0]);
                 g.tin = tab_of(sj.ins[0]);
                 g.scale_px = sj.op == OP_UPSAMPLE ? sj.p[P_SCALE] : 1;
+                g.shift = -1;
                 g.scale = sj.op == OP_CHSCALE ? static_cast<const float*>(ptr_of(sj.ins[1])) : nullptr;
                 g.scale_c = sj.op == OP_CHSCALE ? pd.values[sj.ins[1]].channels : 0;
                 g.residual = sj.op == OP_CHSCALE ? sj.p[P_RESIDUAL] : 0;
@@ -585,7 +586,9 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
             }
             if (n >= 2) {
                 std::sort(src, src + n, [](const GatherSrc& a, const GatherSrc& b) { return a.out < b.out; });
-                launch_concat_gather(src, n, tab_of(s.out), cx.n_img, geo_of(s.out).max_pix, stream);
+                int mh = 0, mw = 0;
+                for (const ImgTab& t : geo_of(s.out).tab) { mh = std::max(mh, t.h); mw = std::max(mw, t.w); }
+                launch_concat_gather(src, n, tab_of(s.out), cx.n_img, mh, mw, stream);
                 launches++;
                 cx.kind[k] = 2;
                 for (size_t q = k + 1; q < j; q++) {

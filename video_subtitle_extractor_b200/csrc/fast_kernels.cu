@@ -577,37 +577,46 @@ struct GatherDev {
 };
 
 __global__ void __launch_bounds__(256) concat_gather_kernel(GatherDev p) {
-    const int img = blockIdx.y;
+    // grid: x over (column, 16-byte piece) of one output row, y = row, z = image: one integer division per thread
+    const int img = blockIdx.z, oy = blockIdx.y;
     const ImgTab to = p.tout[img];
-    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= int64_t(to.h) * to.w * p.total_cvecs) return;
-    int piece = int(idx % p.total_cvecs);
-    const int m = int(idx / p.total_cvecs);
-    const int oy = m / to.w, ox = m - oy * to.w;
+    if (oy >= to.h) return;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= to.w * p.total_cvecs) return;
+    const int ox = l / p.total_cvecs;
+    int piece = l - ox * p.total_cvecs;
     int k = 0;
     while (k + 1 < p.n && piece >= p.s[k].cvecs) { piece -= p.s[k].cvecs; k++; }
     const GatherSrc& g = p.s[k];
     const ImgTab ti = g.tin[img];
-    const int iy = oy / g.scale_px, ix = ox / g.scale_px;
+    const int iy = g.shift >= 0 ? oy >> g.shift : oy / g.scale_px, ix = g.shift >= 0 ? ox >> g.shift : ox / g.scale_px;
     float x[8];
     load8h(g.in + (size_t(ti.off) + size_t(iy) * ti.w + ix) * g.in_cs + piece * 8, x);
     if (g.scale) {
+        const float* sp = g.scale + size_t(img) * g.scale_c;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int c = piece * 8 + j;
-            const float sc = c < g.scale_c ? g.scale[size_t(img) * g.scale_c + c] : 0.f;
+            const float sc = c < g.scale_c ? sp[c] : 0.f;
             x[j] = g.residual ? x[j] + x[j] * sc : x[j] * sc;
         }
     }
-    store8h(g.out + (size_t(to.off) + m) * g.out_cs + piece * 8, x);
+    store8h(g.out + (size_t(to.off) + size_t(oy) * to.w + ox) * g.out_cs + piece * 8, x);
 }
 
-void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_pix, cudaStream_t st) {
+void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_h, int max_out_w, cudaStream_t st) {
     GatherDev d{};
     d.n = n;
     d.tout = tout;
-    for (int i = 0; i < n; i++) { d.s[i] = src[i]; d.total_cvecs += src[i].cvecs; }
-    dim3 grid(cdiv_i(int64_t(max_out_pix) * d.total_cvecs, 256), n_img);
+    for (int i = 0; i < n; i++) {
+        d.s[i] = src[i];
+        d.total_cvecs += src[i].cvecs;
+        int sh = -1;
+        for (int b2 = 0; b2 < 8; b2++)
+            if ((1 << b2) == src[i].scale_px) sh = b2;
+        d.s[i].shift = sh;
+    }
+    dim3 grid(cdiv_i(int64_t(max_out_w) * d.total_cvecs, 256), max_out_h, n_img);
     concat_gather_kernel<<<grid, 256, 0, st>>>(d);
 }
 

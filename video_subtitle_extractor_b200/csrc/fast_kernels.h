@@ -32,10 +32,10 @@ void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, 
 // one source of a concat gather: a channel slice of the output filled from `in` (nearest-upsampled by scale_px, and/or
 // multiplied by a per-image channel gate as CHSCALE does).  Sources must be ordered by ascending slice offset.
 struct GatherSrc {
-    const __half* in; int in_cs; const ImgTab* tin; int scale_px;
+    const __half* in; int in_cs; const ImgTab* tin; int scale_px; int shift;   // shift: log2(scale_px) or -1 (set by the launcher)
     const float* scale; int scale_c; int residual;     // optional channel gate (nullptr = plain copy)
     __half* out; int out_cs; int cvecs;                // slice base pointer, row pitch of the concat buffer, slice width / 8
 };
-void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_pix, cudaStream_t st);
+void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_h, int max_out_w, cudaStream_t st);
 
 }  // namespace vse
