@@ -155,8 +155,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {args.height}p subtitle frames, {DET} + {REC}, CPU restatement of the reference path",
-                   "frames_per_step": per_step},
+        "config": {"workload": f"synthetic {args.height}p subtitle frames (SURVEY.md §8d generator), {DET} + {REC}",
+                   "frames_per_step_per_gpu": args.batch, "frame": [args.height, args.width, 3],
+                   "arm": "CPU restatement of the reference path (torch-CPU fp32 + cv2, all host threads), bounded sample: "
+                          f"{per_step} of the {args.batch} frames of each step"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -28,10 +28,10 @@ Engine::Engine(const vse_config& c) : cfg(c) {
                                           std::to_string(prop.major) + "." + std::to_string(prop.minor)};
 }
 
-size_t Engine::elt_size(const ValueRec& v) const {
+size_t Engine::elt_size(int which, const ValueRec& v) const {
     if (v.dtype == DT_U8) return 1;
     if (v.dtype == DT_F32) return 4;
-    return cfg.precision == VSE_PRECISION_FP32 ? 4 : 2;
+    return plan_prec_[which] == VSE_PRECISION_FP32 ? 4 : 2;
 }
 
 int Engine::value_cs(const PlanData& pd, int vid) const {
@@ -53,11 +53,14 @@ void Engine::load_plan(int which, const void* blob, size_t n) {
     last_tab_[which].clear();
     std::string err = lp.data.parse(blob, n);
     if (!err.empty()) throw InvalidArg{err};
-    prepare_plan(lp);
+    // activation type of this plan: the engine's, except that VSE_FLAG_DET_FP32 keeps the detector in fp32 (server detector
+    // V4/ch_det: activations beyond the fp16 range) while the recogniser stays on the fp16 tensor-core path
+    plan_prec_[which] = (which == 0 && (cfg.flags & VSE_FLAG_DET_FP32)) ? int(VSE_PRECISION_FP32) : cfg.precision;
+    prepare_plan(which, lp);
     lp.loaded = true;
 }
 
-void Engine::prepare_plan(LoadedPlan& lp) {
+void Engine::prepare_plan(int which, LoadedPlan& lp) {
     const PlanData& pd = lp.data;
     std::vector<float> host;
     host.reserve(pd.weights.size() * 2 + 4096);
@@ -104,7 +107,7 @@ void Engine::prepare_plan(LoadedPlan& lp) {
                 // pixel-packed variant (gemm_tc.h): narrow 1x1 convs whose input pixels are 32 / 64 contiguous bytes and whose
                 // output is a dense value (not a slice of a concat buffer)
                 if (s.op == OP_CONV && kh == 1 && kw == 1 && s.p[P_SH] == 1 && s.p[P_SW] == 1 && s.p[P_PH] == 0 && s.p[P_PW] == 0 &&
-                    cfg.precision == VSE_PRECISION_FP16 && !(cfg.flags & (VSE_FLAG_NO_TENSOR_CORES | VSE_FLAG_NO_PIXEL_PACK)) &&
+                    plan_prec_[which] == VSE_PRECISION_FP16 && !(cfg.flags & (VSE_FLAG_NO_TENSOR_CORES | VSE_FLAG_NO_PIXEL_PACK)) &&
                     s.ins[0] != pd.hdr.input_vid && pd.values[s.out].dtype != DT_F32) {
                     const int ics = value_cs(pd, s.ins[0]), ocs = value_cs(pd, s.out);
                     const bool res_ok = !s.p[P_HAS_RES] || value_cs(pd, s.ins[1]) == ocs;
@@ -197,7 +200,7 @@ void Engine::prepare_plan(LoadedPlan& lp) {
     lp.tcw_off.assign(pd.steps.size(), 0);
     lp.tcw_pk.assign(pd.steps.size(), TcWeights{});
     lp.tcw_pk_off.assign(pd.steps.size(), 0);
-    if (cfg.precision == VSE_PRECISION_FP16 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
+    if (plan_prec_[which] == VSE_PRECISION_FP16 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
         std::vector<uint16_t> all;
         auto append = [&](TcWeights& t) -> size_t {
             while (all.size() % 512) all.push_back(0);   // 1024-byte aligned matrices
@@ -425,7 +428,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         if (r.kind == KIND_VEC) return size_t(cx.n_img) * r.channels * sizeof(float);
         int g = cx.vals[v].geo;
         if (g < 0) throw InvalidArg{"value without geometry: " + std::to_string(v)};
-        return size_t(cx.geos[g].total) * value_cs(pd, v) * elt_size(r);
+        return size_t(cx.geos[g].total) * value_cs(pd, v) * elt_size(which, r);
     };
     const int nsteps = int(pd.steps.size());
     for (int k = -1; k <= nsteps; k++) {
@@ -487,7 +490,7 @@ void* Engine::vptr(int which, int vid) const {
     int r = v.alias_of >= 0 ? v.alias_of : vid;
     const ValueRt& rt = ctx_[which].vals[r];
     char* base = static_cast<char*>(arena_[which].p) + rt.off;
-    if (v.alias_of >= 0) base += size_t(v.alias_coff) * elt_size(pd.values[r]);
+    if (v.alias_of >= 0) base += size_t(v.alias_coff) * elt_size(which, pd.values[r]);
     return base;
 }
 
@@ -525,7 +528,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
     LoadedPlan& lp = plans_[which];
     const PlanData& pd = lp.data;
     ExecContext& cx = ctx_[which];
-    const int prec = cfg.precision == VSE_PRECISION_FP32 ? 1 : 0;
+    const int prec = plan_prec_[which] == VSE_PRECISION_FP32 ? 1 : 0;
     const ImgTab* dtab = cx.tabs.as<ImgTab>();
     auto tab_of = [&](int vid) -> const ImgTab* {
         int g = cx.vals[vid].geo;
@@ -758,7 +761,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
             case OP_COPY: {
                 // copy ins[0] into channels [coff, coff+c) of the concat root `out`
                 const int coff = s.p[P_SCALE], c = s.p[P_COUT];
-                char* dst = static_cast<char*>(ptr_of(s.out)) + size_t(coff) * elt_size(vo);
+                char* dst = static_cast<char*>(ptr_of(s.out)) + size_t(coff) * elt_size(which, vo);
                 if (coff % 8 == 0) {
                     launch_copy(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), dst, value_cs(pd, s.out), pad8(c), geo_of(s.ins[0]).total,
                                 prec, stream);
@@ -839,8 +842,8 @@ int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
         o[3] = s.ins[0] >= 0 ? pd.values[s.ins[0]].channels : 0;
         o[4] = pd.values[s.out].channels;
         o[5] = (s.op == OP_CONV || s.op == OP_STEM || s.op == OP_DWCONV) ? s.p[P_KH] * s.p[P_KW] : (s.op == OP_DECONV2 ? 4 : 1);
-        o[6] = s.ins[0] >= 0 ? int64_t(elt_size(pd.values[s.ins[0]])) : 0;
-        o[7] = int64_t(elt_size(pd.values[s.out]));
+        o[6] = s.ins[0] >= 0 ? int64_t(elt_size(which, pd.values[s.ins[0]])) : 0;
+        o[7] = int64_t(elt_size(which, pd.values[s.out]));
     }
     return n;
 }
@@ -884,7 +887,7 @@ int64_t Engine::get_value(int which, int vid, float* out, int64_t cap, int32_t* 
     if (cap < n) throw InvalidArg{"output buffer too small"};
     if (v.dtype == DT_U8) throw InvalidArg{"cannot dump the uint8 input"};
     dbg_.reserve(size_t(n) * sizeof(float));
-    const int prec = cfg.precision == VSE_PRECISION_FP32 ? 1 : 0;
+    const int prec = plan_prec_[which] == VSE_PRECISION_FP32 ? 1 : 0;
     bool is_f32 = v.dtype == DT_F32 || v.kind == KIND_VEC;
     launch_to_float(vptr(which, vid), value_cs(pd, vid), is_f32, dbg_.as<float>(), v.channels, pixels, prec, stream);
     VSE_CUDA(cudaMemcpyAsync(out, dbg_.p, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, stream));

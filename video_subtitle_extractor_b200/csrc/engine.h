@@ -176,10 +176,11 @@ class Engine {
     int64_t tc_launches = 0;
 
   private:
-    void prepare_plan(LoadedPlan& lp);
+    void prepare_plan(int which, LoadedPlan& lp);
     void build_context(int which, const std::vector<ImgTab>& in_tab, bool keep_all);
     void exec_steps(int which, std::vector<cudaEvent_t>* step_events = nullptr);
-    size_t elt_size(const ValueRec& v) const;
+    size_t elt_size(int which, const ValueRec& v) const;
+    int plan_prec_[2] = {0, 0};   // VSE_PRECISION_* per plan (see load_plan)
     int value_cs(const PlanData& pd, int vid) const;  // channel stride in elements
     void* vptr(int which, int vid) const;
     bool launch_conv(int which, int step, const ConvArgs& a, int prec);   // true: ran on the tcgen05 kernel

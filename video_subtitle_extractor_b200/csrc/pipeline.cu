@@ -170,7 +170,7 @@ void Engine::db_post_device(const float* prob, const std::vector<DetFrame>& fram
         if (status[i] & 4)
             throw StateError{"frame " + std::to_string(i) + ": the detection map holds non-finite values — this model's activations "
                              "exceed the fp16 range (e.g. V4/ch_det: LK-PAN outputs reach 1.5e5); create the engine with "
-                             "VSE_PRECISION_FP32 for it"};
+                             "VSE_FLAG_DET_FP32 (or VSE_PRECISION_FP32) for it"};
         if (status[i] & 1) throw InvalidArg{"frame " + std::to_string(i) + ": more than 4096 connected components in the detection map"};
         if (status[i] & 2) throw CapacityError{"frame " + std::to_string(i) + ": more boxes than max_boxes_per_frame"};
     }

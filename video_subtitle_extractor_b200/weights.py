@@ -23,6 +23,14 @@ def _path(name: str) -> str:
     return os.path.join(WEIGHTS_DIR, name.replace("/", "__") + ".vsep")
 
 
+# models whose activations exceed the fp16 range: the engine must be created with fp32 activations
+FP32_ONLY = {"V4/ch_det"}
+
+
+def needs_fp32(name: str) -> bool:
+    return "/".join(name.replace("\\", "/").rstrip("/").split("/")[-2:]) in FP32_ONLY
+
+
 def is_det(name: str) -> bool:
     return "_det" in name
 
