@@ -276,11 +276,8 @@ static bool dw_tile_launch(const DwDev& d, const ConvArgs& a, int max_h, int max
     const int tiles_x = (max_w + 15) / 16, tiles_y = (max_h + TH - 1) / TH;
     dim3 grid(tiles_x * tiles_y, a.n_img, (d.cvecs + CBV - 1) / CBV);
     auto go = [&](auto kern) {
-        static bool configured = false;   // one static per instantiation of this lambda's enclosing template + kernel
-        if (smem > 48 * 1024 && !configured) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            configured = true;
-        }
+        // > 48 KB of dynamic shared memory needs the opt-in (per device and per kernel instantiation; the call is cheap)
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         kern<<<grid, TH * 4 * CBV, smem, st>>>(d, tiles_x);
     };
     switch (a.epi.act) {

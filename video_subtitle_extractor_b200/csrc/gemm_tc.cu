@@ -804,10 +804,12 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     p.res = t.epi.res; p.res_cs = t.epi.res_cs; p.act = t.epi.act; p.act2 = t.epi.act2;
     p.hs_slope = t.epi.hs_slope; p.hs_offset = t.epi.hs_offset;
     const size_t smem = size_t(p.stages) * stage_bytes + p.b_total + kOutBufs * kOutBufBytes + 1024 + kBarRegion + param_bytes;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int total = t.num_m_tiles * t.n_chunks;
     const int grid = std::max(1, std::min(total, sm_count));
