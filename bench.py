@@ -334,6 +334,9 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.stop()
     wall_e2e, dev_s_e2e, _, _, last_e2e = timed(host_batches, E.MEM_PINNED)
     stage_ms = [float(x) for x in eng.last_timings]
+    # one extra un-prefetched call: its stage 0 is the bare host->device copy time of one batch on this box (PCIe rate)
+    step(host_batches, 1, E.MEM_PINNED)
+    h2d_alone_ms = float(eng.last_timings[0])
 
     wall_max = shard.max_over_ranks(wall, dev)
     wall_e2e_max = shard.max_over_ranks(wall_e2e, dev)
@@ -379,6 +382,7 @@ def run_b200(args, rank, local_rank, world):
             "device_ms_per_step": dev_s / args.steps * 1e3, "stage_ms_last_e2e_step": stage_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_max / args.steps * 1e3, "device_ms_per_step": dev_s_e2e / args.steps * 1e3,
+                    "h2d_ms_per_step_alone": h2d_alone_ms, "h2d_gbs": B * frame_bytes / max(h2d_alone_ms, 1e-6) / 1e6,
                     "overlap": "vse_prefetch: the copy of step k+1 is issued before step k runs (copy stream)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }

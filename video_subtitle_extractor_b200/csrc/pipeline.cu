@@ -28,14 +28,14 @@ struct Engine::Pipeline {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t fdone[2] = {nullptr, nullptr};
     std::vector<Pending> pending;             // oldest first, at most 2
-    DevBuf labels, slot_of, n_comp, roots, bbox, order, cand, status, n_boxes, quads, scores;
+    DevBuf labels, slot_of, n_comp, roots, bbox, order, cand, status, n_boxes, quads, scores, blk_fg;
     DevBuf cubic_tab, crop_jobs, crop_buf, rec_jobs, rec_in;
     DevBuf ctc_meta, ctc_ids, ctc_len, ctc_score;
     PinnedBuf h_in, h_out;
     cudaEvent_t ev[9] = {};
     bool ev_ready = false, tab_ready = false;
     std::vector<DevBuf*> all() {
-        return {&fbuf[0], &fbuf[1], &dbg_frames, &det_in, &jobs, &det_frames, &labels, &slot_of, &n_comp, &roots, &bbox, &order, &cand, &status,
+        return {&fbuf[0], &fbuf[1], &dbg_frames, &det_in, &jobs, &det_frames, &labels, &slot_of, &n_comp, &roots, &bbox, &order, &cand, &status, &blk_fg,
                 &n_boxes, &quads, &scores, &cubic_tab, &crop_jobs, &crop_buf, &rec_jobs, &rec_in, &ctc_meta, &ctc_ids,
                 &ctc_len, &ctc_score};
     }
@@ -112,6 +112,8 @@ static DbWorkspace make_ws(Engine::Pipeline* p) {
     DbWorkspace ws;
     ws.labels = p->labels.as<int>();
     ws.slot_of = p->slot_of.as<int>();
+    ws.fg_count = p->blk_fg.as<int>();
+    ws.fg_list = p->blk_fg.as<int>() + 4;
     ws.n_comp = p->n_comp.as<int>();
     ws.roots = p->roots.as<int>();
     ws.bbox = p->bbox.as<int>();
@@ -137,9 +139,11 @@ void Engine::db_post_device(const float* prob, const std::vector<DetFrame>& fram
         total = std::max(total, size_t(f.map_off) + size_t(f.rh) * f.rw);
     }
     if (max_rh > 2048) throw InvalidArg{"detection map taller than 2048 rows"};
+    if (max_rw > 32 * 1023 || n > 2047) throw InvalidArg{"detection batch beyond the post-process limits (2047 frames, 32736 columns)"};
     const int mb = cfg.max_boxes_per_frame, mc = std::min(std::max(cfg.det_max_candidates, 1), kSlotCap);
     P->labels.reserve(total * sizeof(int));
     P->slot_of.reserve(total * sizeof(int));
+    P->blk_fg.reserve((size_t(n) * ((max_rh + 7) / 8) * ((max_rw + 31) / 32) + 4) * sizeof(int));
     P->n_comp.reserve(n * sizeof(int));
     P->status.reserve(n * sizeof(int));
     P->roots.reserve(size_t(n) * kSlotCap * sizeof(int));

@@ -52,7 +52,8 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 // block (32, 8): a warp covers 32 consecutive pixels of one row; the initial label is the start of the pixel's
 // run inside that 32-pixel segment (one ballot, no chains along rows)
 __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ prob, const DetFrame* __restrict__ frames,
-                                                     float thresh, int* __restrict__ labels, int* __restrict__ status) {
+                                                     float thresh, int* __restrict__ labels, int* __restrict__ status,
+                                                     int* __restrict__ fg_count, int* __restrict__ fg_list) {
     const DetFrame fr = frames[blockIdx.z];
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const bool in = x < fr.rw && y < fr.rh;
@@ -66,6 +67,12 @@ __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ p
         if (!(fabsf(pv) <= 1.5f)) atomicOr(&status[blockIdx.z], 4);
     }
     const unsigned mask = __ballot_sync(0xffffffffu, fg);
+    // subtitle frames are > 99 % background: the later labelling passes skip blocks without foreground
+    const int any = __syncthreads_or(fg ? 1 : 0);
+    if (any && threadIdx.x == 0 && threadIdx.y == 0) {
+        const int slot = atomicAdd(fg_count, 1);      // order of the list does not matter: the passes below are order-free
+        fg_list[slot] = (blockIdx.z << 20) | (blockIdx.y << 10) | blockIdx.x;
+    }
     if (!in) return;
     if (fg) {
         const int lane = threadIdx.x;
@@ -77,12 +84,16 @@ __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ p
     }
 }
 
-__global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict__ frames, int* labels) {
-    const DetFrame fr = frames[blockIdx.z];
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= fr.rw || y >= fr.rh) return;
+__global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict__ frames, int* labels,
+                                                      const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+  const int n_fg = *fg_count;
+  for (int it = blockIdx.x; it < n_fg; it += gridDim.x) {
+    const int code = fg_list[it], bz = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
+    const DetFrame fr = frames[bz];
+    const int x = bx * 32 + threadIdx.x, y = by * blockDim.y + threadIdx.y;
+    if (x >= fr.rw || y >= fr.rh) continue;
     const int g = fr.map_off + y * fr.rw + x;
-    if (labels[g] < 0) return;
+    if (labels[g] < 0) continue;
     const int rw = fr.rw;
     const bool W = x > 0 && labels[g - 1] >= 0;
     const bool up = y > 0;
@@ -100,16 +111,20 @@ __global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict
             if (NE) uf_union(labels, g, g - rw + 1);
         }
     }
+  }
 }
 
 __global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restrict__ frames, int* labels, int* slot_of,
-                                                        int* n_comp, int* roots, int* bbox) {
-    const int f = blockIdx.z;
+                                                        int* n_comp, int* roots, int* bbox,
+                                                        const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+  const int n_fg = *fg_count;
+  for (int it = blockIdx.x; it < n_fg; it += gridDim.x) {
+    const int code = fg_list[it], f = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
     const DetFrame fr = frames[f];
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= fr.rw || y >= fr.rh) return;
+    const int x = bx * 32 + threadIdx.x, y = by * blockDim.y + threadIdx.y;
+    if (x >= fr.rw || y >= fr.rh) continue;
     const int g = fr.map_off + y * fr.rw + x;
-    if (labels[g] < 0) return;
+    if (labels[g] < 0) continue;
     const int r = uf_find(labels, g);
     labels[g] = r;
     if (r == g) {
@@ -123,22 +138,26 @@ __global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restri
             slot_of[g] = -1;
         }
     }
+  }
 }
 
 __global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ frames, const int* __restrict__ labels,
-                                               const int* __restrict__ slot_of, int* bbox) {
-    const int f = blockIdx.z;
+                                               const int* __restrict__ slot_of, int* bbox,
+                                               const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+  const int n_fg = *fg_count;
+  for (int it = blockIdx.x; it < n_fg; it += gridDim.x) {
+    const int code = fg_list[it], f = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
     const DetFrame fr = frames[f];
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= fr.rw || y >= fr.rh) return;
+    const int x = bx * 32 + threadIdx.x, y = by * blockDim.y + threadIdx.y;
+    if (x >= fr.rw || y >= fr.rh) continue;
     const int g = fr.map_off + y * fr.rw + x;
     const int r = labels[g];
-    if (r < 0) return;
+    if (r < 0) continue;
     const bool W = x > 0 && labels[g - 1] >= 0;
     const bool E = x + 1 < fr.rw && labels[g + 1] >= 0;
-    if (W && E) return;
+    if (W && E) continue;
     const int slot = slot_of[r];
-    if (slot < 0) return;
+    if (slot < 0) continue;
     int* b = bbox + (size_t(f) * kSlotCap + slot) * 4;
     if (!W) {
         atomicMin(b + 0, x);
@@ -146,6 +165,7 @@ __global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ fram
         atomicMax(b + 3, y);
     }
     if (!E) atomicMax(b + 2, x);
+  }
 }
 
 // cv2.findContours(RETR_LIST) returns contours in reverse discovery order: descending root (raster) index
@@ -323,10 +343,15 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
     cudaMemsetAsync(ws.n_comp, 0, sizeof(int) * n_frames, st);
     cudaMemsetAsync(ws.status, 0, sizeof(int) * n_frames, st);
     dim3 blk(32, 8), grid((max_rw + 31) / 32, (max_rh + 7) / 8, n_frames);
-    db_label_init<<<grid, blk, 0, st>>>(prob, frames_dev, p.thresh, ws.labels, ws.status);
-    db_label_merge<<<grid, blk, 0, st>>>(frames_dev, ws.labels);
-    db_label_flatten<<<grid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox);
-    db_bbox<<<grid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.bbox);
+    // (32 x 8)-pixel blocks that hold foreground are listed by the first pass; the other passes walk that list with a
+    // machine-sized grid (subtitle maps are > 99 % background, and launching 65 k empty blocks costs more than the work)
+    if (grid.x > 1023 || grid.y > 1023 || n_frames > 2047) return;   // list code = frame << 20 | block_y << 10 | block_x (checked by the caller)
+    cudaMemsetAsync(ws.fg_count, 0, sizeof(int), st);
+    db_label_init<<<grid, blk, 0, st>>>(prob, frames_dev, p.thresh, ws.labels, ws.status, ws.fg_count, ws.fg_list);
+    const int pgrid = 148 * 4;
+    db_label_merge<<<pgrid, blk, 0, st>>>(frames_dev, ws.labels, ws.fg_count, ws.fg_list);
+    db_label_flatten<<<pgrid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox, ws.fg_count, ws.fg_list);
+    db_bbox<<<pgrid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.bbox, ws.fg_count, ws.fg_list);
     db_sort_components<<<n_frames, 256, 0, st>>>(ws.n_comp, ws.roots, ws.order, ws.status);
     size_t smem = db_candidate_smem_bytes(max_rh);
     static size_t configured = 0;

@@ -32,7 +32,9 @@ struct DbWorkspace {
     int* bbox;        // [n_frames][kSlotCap][4] xmin, ymin, xmax, ymax (map coordinates)
     int* order;       // [n_frames][kSlotCap] slots in cv2 contour order
     float* cand;      // [n_frames][max_candidates][10]: valid, score, quad[8]
-    int* status;      // [n_frames] bit 0: too many components, bit 1: too many boxes
+    int* status;      // [n_frames] bit 0: too many components, bit 1: too many boxes, bit 2: non-finite probability
+    int* fg_count;    // [1] number of (32 x 8)-pixel blocks that hold foreground
+    int* fg_list;     // [n_frames * blocks_y * blocks_x] their codes (frame << 20 | block_y << 10 | block_x)
     // outputs
     int* n_boxes;     // [n_frames]
     float* quads;     // [n_frames][max_boxes][8]
