@@ -44,7 +44,11 @@ typedef enum {
 
 enum { VSE_MEM_HOST = 0, VSE_MEM_PINNED = 1, VSE_MEM_DEVICE = 2 };
 enum { VSE_PLAN_DET = 0, VSE_PLAN_REC = 1 };
-enum { VSE_PRECISION_FP16 = 0, VSE_PRECISION_FP32 = 1 };
+enum {
+    VSE_PRECISION_FP16 = 0, /* fp16 activations, fp32 accumulate: tcgen05 kind::f16 convolutions + specialised kernels   */
+    VSE_PRECISION_FP32 = 1, /* fp32 activations, CUDA-core kernels only: the exact-parity mode                             */
+    VSE_PRECISION_TF32 = 2  /* fp32 activations (full range), convolutions on tcgen05 kind::tf32 (10-bit mantissa operands) */
+};
 enum {
     VSE_FLAG_NO_TENSOR_CORES = 1, /* vse_config.flags: keep every conv on the CUDA-core kernels (A/B checks)      */
     VSE_FLAG_NO_FAST_KERNELS = 2, /* keep depthwise / stem / DB-head / SE steps on the generic kernels (A/B checks) */
@@ -54,7 +58,8 @@ enum {
     VSE_FLAG_NO_CONCAT_GATHER = 256, VSE_FLAG_NO_HALO = 512,
     /* not an A/B switch: run the DETECTOR plan with fp32 activations whatever vse_config.precision says (V4/ch_det, the
      * accurate-mode detector of backend/tools/paddle_model_config.py:60,70, exceeds the fp16 range) */
-    VSE_FLAG_DET_FP32 = 1024
+    VSE_FLAG_DET_FP32 = 1024,
+    VSE_FLAG_DET_TF32 = 2048   /* same, with the detector's convolutions on the tf32 tensor-core path */
 };
 
 /* Mirrors the knobs the reference passes to PaddleOCR / TextDetector (ocr.py:91-113) and the

@@ -34,8 +34,10 @@ def interp_values(plan: P.Plan, images_bgr: Sequence[np.ndarray], valid_w: Seque
     return {vid: np.concatenate(parts, 0) for vid, parts in per_value.items()}
 
 
-def compare_all(engine, which: int, plan: P.Plan, images_bgr: Sequence[np.ndarray], valid_w: Optional[Sequence[int]] = None):
-    """-> list of (step index, op name, out vid, max abs err, ref max abs) for every materialised step output."""
+def compare_all(engine, which: int, plan: P.Plan, images_bgr: Sequence[np.ndarray], valid_w: Optional[Sequence[int]] = None,
+                keep: Optional[dict] = None):
+    """-> list of (step index, op name, out vid, max abs err, ref max abs) for every materialised step output.
+    `keep`: optional dict; filled with {vid: (engine array, interpreter array)} for the plan's output values."""
     valid_w = list(valid_w) if valid_w is not None else [im.shape[1] for im in images_bgr]
     ref = interp_values(plan, images_bgr, valid_w)
     engine.debug_run_plan(which, [to_bgrx(im) for im in images_bgr], valid_w, keep_all=True)
@@ -52,4 +54,6 @@ def compare_all(engine, which: int, plan: P.Plan, images_bgr: Sequence[np.ndarra
             report.append((k, P.OP_NAMES[s.op], s.out, float("inf"), float(np.abs(want).max())))
             continue
         report.append((k, P.OP_NAMES[s.op], s.out, float(np.abs(got - want).max()), float(np.abs(want).max())))
+        if keep is not None and s.out in plan.output_vids:
+            keep[s.out] = (got, want)
     return report

@@ -33,7 +33,7 @@ class PaddleOCR:
         shape = [int(v) for v in str(rec_image_shape).split(",")]
         self.drop_score = drop_score
         # accurate mode's server detector (paddle_model_config.py:60,70) overflows fp16 activations: fp32 engine for it
-        flags = _E.FLAG_DET_FP32 if det_model_dir and _W.needs_fp32(det_model_dir) else 0
+        flags = _E.FLAG_DET_TF32 if det_model_dir and _W.needs_fp32(det_model_dir) else 0
         self.engine = _E.Engine(device=gpu_id, flags=flags, rec_image_h=shape[1], rec_image_w=shape[2], rec_batch_num=rec_batch_num,
                                 det_limit_side_len=det_limit_side_len, det_thresh=det_db_thresh,
                                 det_box_thresh=det_db_box_thresh, det_unclip_ratio=det_db_unclip_ratio)

@@ -31,7 +31,7 @@ Engine::Engine(const vse_config& c) : cfg(c) {
 size_t Engine::elt_size(int which, const ValueRec& v) const {
     if (v.dtype == DT_U8) return 1;
     if (v.dtype == DT_F32) return 4;
-    return plan_prec_[which] == VSE_PRECISION_FP32 ? 4 : 2;
+    return plan_prec_[which] == VSE_PRECISION_FP16 ? 2 : 4;
 }
 
 int Engine::value_cs(const PlanData& pd, int vid) const {
@@ -55,7 +55,10 @@ void Engine::load_plan(int which, const void* blob, size_t n) {
     if (!err.empty()) throw InvalidArg{err};
     // activation type of this plan: the engine's, except that VSE_FLAG_DET_FP32 keeps the detector in fp32 (server detector
     // V4/ch_det: activations beyond the fp16 range) while the recogniser stays on the fp16 tensor-core path
-    plan_prec_[which] = (which == 0 && (cfg.flags & VSE_FLAG_DET_FP32)) ? int(VSE_PRECISION_FP32) : cfg.precision;
+    plan_prec_[which] = cfg.precision;
+    if (which == 0 && (cfg.flags & VSE_FLAG_DET_FP32)) plan_prec_[which] = VSE_PRECISION_FP32;
+    if (which == 0 && (cfg.flags & VSE_FLAG_DET_TF32)) plan_prec_[which] = VSE_PRECISION_TF32;
+    if (plan_prec_[which] < VSE_PRECISION_FP16 || plan_prec_[which] > VSE_PRECISION_TF32) throw InvalidArg{"bad precision"};
     prepare_plan(which, lp);
     lp.loaded = true;
 }
@@ -200,7 +203,8 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
     lp.tcw_off.assign(pd.steps.size(), 0);
     lp.tcw_pk.assign(pd.steps.size(), TcWeights{});
     lp.tcw_pk_off.assign(pd.steps.size(), 0);
-    if (plan_prec_[which] == VSE_PRECISION_FP16 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
+    if (plan_prec_[which] != VSE_PRECISION_FP32 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
+        const bool tf32 = plan_prec_[which] == VSE_PRECISION_TF32;
         std::vector<uint16_t> all;
         auto append = [&](TcWeights& t) -> size_t {
             while (all.size() % 512) all.push_back(0);   // 1024-byte aligned matrices
@@ -213,7 +217,7 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
         for (size_t k = 0; k < pd.steps.size(); k++) {
             const StepRec& s = pd.steps[k];
             if (s.op != OP_CONV || s.p[P_SH] != 1 || s.p[P_SW] != 1) continue;
-            lp.tcw[k] = tc_pack_weights(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], s.p[P_KH] * s.p[P_KW]);
+            lp.tcw[k] = tc_pack_weights(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], s.p[P_KH] * s.p[P_KW], tf32);
             lp.tcw_off[k] = append(lp.tcw[k]);
             if (lp.dev[k].pack > 0) {
                 lp.tcw_pk[k] = tc_pack_weights_pixelpacked(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], value_cs(pd, s.ins[0]),
@@ -528,7 +532,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
     LoadedPlan& lp = plans_[which];
     const PlanData& pd = lp.data;
     ExecContext& cx = ctx_[which];
-    const int prec = plan_prec_[which] == VSE_PRECISION_FP32 ? 1 : 0;
+    const int prec = plan_prec_[which] == VSE_PRECISION_FP16 ? 0 : 1;   // storage type of activations: __half / float
     const ImgTab* dtab = cx.tabs.as<ImgTab>();
     auto tab_of = [&](int vid) -> const ImgTab* {
         int g = cx.vals[vid].geo;
@@ -850,7 +854,8 @@ int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
 
 bool Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
     TcConv& t = ctx_[which].tc[step];
-    if (prec == 0 && t.valid) {
+    (void)prec;
+    if (t.valid) {   // built only for plans whose precision uses the tensor cores (fp16 / tf32)
         t.out = a.out;
         t.out_cs = a.out_cs;
         t.n_store = a.cout_store;
@@ -887,7 +892,7 @@ int64_t Engine::get_value(int which, int vid, float* out, int64_t cap, int32_t* 
     if (cap < n) throw InvalidArg{"output buffer too small"};
     if (v.dtype == DT_U8) throw InvalidArg{"cannot dump the uint8 input"};
     dbg_.reserve(size_t(n) * sizeof(float));
-    const int prec = plan_prec_[which] == VSE_PRECISION_FP32 ? 1 : 0;
+    const int prec = plan_prec_[which] == VSE_PRECISION_FP16 ? 0 : 1;   // storage type of activations: __half / float
     bool is_f32 = v.dtype == DT_F32 || v.kind == KIND_VEC;
     launch_to_float(vptr(which, vid), value_cs(pd, vid), is_f32, dbg_.as<float>(), v.channels, pixels, prec, stream);
     VSE_CUDA(cudaMemcpyAsync(out, dbg_.p, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, stream));

@@ -23,7 +23,7 @@
 
 namespace vse {
 
-static constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
+static constexpr int BLOCK_M = 128, BLOCK_K = 64;   // BLOCK_K: fp16 elements per 128-byte K row (32 for fp32 / tf32)
 static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 static constexpr int kEpiWarps = 8;
 static constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -37,7 +37,7 @@ static constexpr int kMaxSmem = 227 * 1024;
 
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
-        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx;
+        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems;
     void* out;
     int out_cs;
     const float* bias;
@@ -189,6 +189,27 @@ __device__ __forceinline__ void umma_f16_words2(uint32_t d_tmem, uint32_t a_lo, 
         "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(a_hi)
         : "memory");
 }
+// kind::tf32: fp32 operands in shared memory (rounded to tf32 by the tensor core), 8 elements (32 bytes) of K per instruction
+__device__ __forceinline__ void umma_tf32_words2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 da, {%1, %6};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(a_hi)
+        : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_words(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+    if constexpr (TF32) umma_tf32_words2(d_tmem, a_lo, a_hi, b_lo, idesc, accumulate);
+    else umma_f16_words2(d_tmem, a_lo, a_hi, b_lo, idesc, accumulate);
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -252,10 +273,10 @@ __device__ __forceinline__ float tc_act(float x, int act, float slope, float off
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// 16 accumulator columns of one output pixel -> 16 fp16 values (two 16-byte pieces)
-template <int ACT, bool POST>
+// 16 accumulator columns of one output pixel -> 16 output values: fp16 (two 16-byte pieces) or fp32 (four pieces)
+template <int ACT, bool POST, bool OUTF32>
 __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* raw, const float* pb, const float* ps,
-                                            const float* pt, int cb, long long pix, uint4* out2) {
+                                            const float* pt, int cb, long long pix, uint4* out4) {
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
@@ -273,22 +294,36 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* r
 #pragma unroll
     for (int h8 = 0; h8 < 2; h8++) {
         if (p.res && pix >= 0 && cb + h8 * 8 < p.n_store) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + size_t(pix) * p.res_cs + cb + h8 * 8);
-            const __half2* rh = reinterpret_cast<const __half2*>(&r4);
+            if constexpr (OUTF32) {
+                const float* rp = static_cast<const float*>(p.res) + size_t(pix) * p.res_cs + cb + h8 * 8;
+                const float4 r0 = ld4(rp), r1 = ld4(rp + 4);
+                v[h8 * 8 + 0] += r0.x; v[h8 * 8 + 1] += r0.y; v[h8 * 8 + 2] += r0.z; v[h8 * 8 + 3] += r0.w;
+                v[h8 * 8 + 4] += r1.x; v[h8 * 8 + 5] += r1.y; v[h8 * 8 + 6] += r1.z; v[h8 * 8 + 7] += r1.w;
+            } else {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + size_t(pix) * p.res_cs + cb + h8 * 8);
+                const __half2* rh = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float2 f = __half22float2(rh[j]);
-                v[h8 * 8 + 2 * j] += f.x;
-                v[h8 * 8 + 2 * j + 1] += f.y;
+                for (int j = 0; j < 4; j++) {
+                    const float2 f = __half22float2(rh[j]);
+                    v[h8 * 8 + 2 * j] += f.x;
+                    v[h8 * 8 + 2 * j + 1] += f.y;
+                }
             }
         }
         if (p.act2 != ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 8; j++) v[h8 * 8 + j] = tc_act(v[h8 * 8 + j], p.act2, 0.f, 0.f);
         }
-        __half2* hh = reinterpret_cast<__half2*>(&out2[h8]);
+        if constexpr (OUTF32) {
+            out4[2 * h8] = make_uint4(__float_as_uint(v[h8 * 8 + 0]), __float_as_uint(v[h8 * 8 + 1]), __float_as_uint(v[h8 * 8 + 2]),
+                                      __float_as_uint(v[h8 * 8 + 3]));
+            out4[2 * h8 + 1] = make_uint4(__float_as_uint(v[h8 * 8 + 4]), __float_as_uint(v[h8 * 8 + 5]), __float_as_uint(v[h8 * 8 + 6]),
+                                          __float_as_uint(v[h8 * 8 + 7]));
+        } else {
+            __half2* hh = reinterpret_cast<__half2*>(&out4[h8]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) hh[j] = __floats2half2_rn(v[h8 * 8 + 2 * j], v[h8 * 8 + 2 * j + 1]);
+            for (int j = 0; j < 4; j++) hh[j] = __floats2half2_rn(v[h8 * 8 + 2 * j], v[h8 * 8 + 2 * j + 1]);
+        }
     }
 }
 
@@ -296,13 +331,14 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* r
 // into a 128B-swizzled [128 pixels x 128 B] staging tile, the warps meet at a named barrier, and one thread hands the tile
 // to TMA (cp.async.bulk.tensor store): full-line, coalesced global writes, rows past the end of the tensor clipped by the
 // hardware.  A ring of kOutBufs staging tiles keeps kOutBufs - 1 stores in flight.
-template <int ACT, bool POST>
+template <int ACT, bool POST, bool OUTF32>
 __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* map_o, uint8_t* sout, uint32_t tmem_base,
                                            uint64_t* tmem_full, uint64_t* tmem_empty, const float* pb, const float* ps,
                                            const float* pt, int q, int half, int lane, bool issuer) {
     const int row = q * 32 + lane;
     const int total_tiles = p.num_m_tiles * p.n_chunks;
-    const int n_sub = (p.n_chunk + 63) >> 6;
+    constexpr int SUBC = OUTF32 ? 32 : 64;        // columns per 128-byte staging row
+    const int n_sub = (p.n_chunk + SUBC - 1) / SUBC;
     const uint32_t sout_addr = smem_u32(sout);
     int acc = 0, slot = 0;
     uint32_t acc_phase = 0;
@@ -327,32 +363,42 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
         const int ch0 = n_idx * p.n_chunk;
         for (int sub = 0; sub < n_sub; sub++) {
-            if (ch0 + sub * 64 >= p.n_store) break;                    // uniform over the 8 warps
-            const int c0 = sub * 64 + half * 32;                        // this warp's 32 columns of the sub-tile
+            if (ch0 + sub * SUBC >= p.n_store) break;                  // uniform over the 8 warps
+            const int c0 = sub * SUBC + half * (SUBC / 2);              // this warp's columns of the sub-tile
             const uint32_t buf = sout_addr + uint32_t(slot * kOutBufBytes) + uint32_t(row * 128);
             if (c0 < p.n_chunk && ch0 + c0 < p.n_store) {               // warp-uniform
-                const bool two = c0 + 16 < p.n_chunk && ch0 + c0 + 16 < p.n_store;
-                uint32_t raw0[16], raw1[16];
-                tmem_ld16_nowait(taddr + uint32_t(c0), raw0);           // .sync.aligned: whole (converged) warp
-                if (two) tmem_ld16_nowait(taddr + uint32_t(c0 + 16), raw1);
-                tmem_ld_wait();
-                uint4 o[2];
-                epi_chunk16<ACT, POST>(p, raw0, pb, ps, pt, ch0 + c0, pix, o);
                 const int j0 = half * 4;                                // 16-byte piece index inside the 128-byte row
-                st_shared_16(buf + uint32_t(((j0 + 0) ^ (row & 7)) << 4), o[0]);
-                st_shared_16(buf + uint32_t(((j0 + 1) ^ (row & 7)) << 4), o[1]);
-                if (two) {
-                    epi_chunk16<ACT, POST>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix, o);
-                    st_shared_16(buf + uint32_t(((j0 + 2) ^ (row & 7)) << 4), o[0]);
-                    st_shared_16(buf + uint32_t(((j0 + 3) ^ (row & 7)) << 4), o[1]);
+                if constexpr (OUTF32) {
+                    uint32_t raw0[16];
+                    tmem_ld16_nowait(taddr + uint32_t(c0), raw0);       // .sync.aligned: whole (converged) warp
+                    tmem_ld_wait();
+                    uint4 o[4];
+                    epi_chunk16<ACT, POST, true>(p, raw0, pb, ps, pt, ch0 + c0, pix, o);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) st_shared_16(buf + uint32_t(((j0 + j) ^ (row & 7)) << 4), o[j]);
+                } else {
+                    const bool two = c0 + 16 < p.n_chunk && ch0 + c0 + 16 < p.n_store;
+                    uint32_t raw0[16], raw1[16];
+                    tmem_ld16_nowait(taddr + uint32_t(c0), raw0);
+                    if (two) tmem_ld16_nowait(taddr + uint32_t(c0 + 16), raw1);
+                    tmem_ld_wait();
+                    uint4 o[2];
+                    epi_chunk16<ACT, POST, false>(p, raw0, pb, ps, pt, ch0 + c0, pix, o);
+                    st_shared_16(buf + uint32_t(((j0 + 0) ^ (row & 7)) << 4), o[0]);
+                    st_shared_16(buf + uint32_t(((j0 + 1) ^ (row & 7)) << 4), o[1]);
+                    if (two) {
+                        epi_chunk16<ACT, POST, false>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix, o);
+                        st_shared_16(buf + uint32_t(((j0 + 2) ^ (row & 7)) << 4), o[0]);
+                        st_shared_16(buf + uint32_t(((j0 + 3) ^ (row & 7)) << 4), o[1]);
+                    }
                 }
                 fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA store
             }
             epi_barrier();
             if (issuer) {
                 const void* src = sout + size_t(slot) * kOutBufBytes;
-                if (p.spatial) tma_store_4d(map_o, src, ch0 + sub * 64, x0, y0, img);
-                else tma_store_2d(map_o, src, ch0 + sub * 64, m_tile * BLOCK_M);
+                if (p.spatial) tma_store_4d(map_o, src, ch0 + sub * SUBC, x0, y0, img);
+                else tma_store_2d(map_o, src, ch0 + sub * SUBC, m_tile * BLOCK_M);
                 tma_store_commit();
                 tma_store_wait_read<kOutBufs - 2>();   // the tile written two barriers from now is free again (see ring note)
             }
@@ -370,7 +416,11 @@ template <bool POST>
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUtensorMap* map_o, uint8_t* sout, uint32_t tmem_base,
                                                   uint64_t* tmem_full, uint64_t* tmem_empty, const float* pb, const float* ps,
                                                   const float* pt, int q, int half, int lane, bool issuer) {
-#define VSE_EPI(A) epilogue_loop<A, POST>(p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer)
+#define VSE_EPI(A)                                                                                                            \
+    do {                                                                                                                      \
+        if (p.tf32) epilogue_loop<A, POST, true>(p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer);  \
+        else epilogue_loop<A, POST, false>(p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer);       \
+    } while (0)
     switch (p.act) {
         case ACT_RELU: VSE_EPI(ACT_RELU); break;
         case ACT_HSWISH: VSE_EPI(ACT_HSWISH); break;
@@ -391,18 +441,20 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUten
 // 2: halo box, KH x KW taps per tile) with the common 3x3 shapes unrolled (KH / KW = 0: run-time extents), and every
 // per-iteration quantity is a running sum instead of a product.
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int KH_, int KW_>
+template <int MODE, int KH_, int KW_, bool TF32>
 __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full, uint64_t* empty, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, uint32_t a_lo0, uint32_t bres_lo,
                                               uint32_t stage16, int k_iters) {
     const int KH = KH_ ? KH_ : p.kh, KW = KW_ ? KW_ : p.kw;
-    const uint32_t idesc = (1u << 4) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+    // instruction descriptor: D = f32, A/B = f16 (kind::f16) or tf32 (kind::tf32, format code 2), N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | (TF32 ? (2u << 7) | (2u << 10) : 0u) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
     const int total_tiles = p.num_m_tiles * p.n_chunks;
     const int stages = p.stages, acc_stages = p.acc_stages, num_kb = p.num_kb, n_chunk = p.n_chunk;
     const bool resident = p.b_resident != 0;
     const uint32_t b_step = uint32_t(n_chunk * 8);                  // one [n_chunk x 64] weight slice in 16-byte units
     const uint32_t a16 = uint32_t(p.a_bytes >> 4);
-    const int ks_last = min(BLOCK_K / UMMA_K, (p.cin - (num_kb - 1) * BLOCK_K + UMMA_K - 1) / UMMA_K);   // all-zero K tail skipped
+    const int umma_k = p.kb_elems / 4;   // K elements per MMA (32 bytes): 16 halves or 8 floats
+    const int ks_last = min(4, (p.cin - (num_kb - 1) * p.kb_elems + umma_k - 1) / umma_k);   // all-zero K tail skipped
     // strides between the weight slices of consecutive taps
     const uint32_t b_ky_step = resident ? uint32_t(KW * num_kb) * b_step : b_step;     // MODE 1
     const uint32_t b_tap_step = resident ? uint32_t(num_kb) * b_step : b_step;         // MODE 2
@@ -422,23 +474,23 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
         for (int it = 0; it < k_iters; it++) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const int ks = (kb == num_kb - 1) ? ks_last : BLOCK_K / UMMA_K;
+            const int ks = (kb == num_kb - 1) ? ks_last : 4;
             const uint32_t b_first = resident ? b_it : a_lo + a16;
             if (elect_one()) {
                 if constexpr (MODE == 0) {
-                    umma_f16_words(d_tmem, a_lo, b_first, idesc, it != 0 ? 1u : 0u);
-                    if (ks > 1) umma_f16_words(d_tmem, a_lo + 2, b_first + 2, idesc, 1u);
-                    if (ks > 2) umma_f16_words(d_tmem, a_lo + 4, b_first + 4, idesc, 1u);
-                    if (ks > 3) umma_f16_words(d_tmem, a_lo + 6, b_first + 6, idesc, 1u);
+                    umma_words<TF32>(d_tmem, a_lo, kDescHi, b_first, idesc, it != 0 ? 1u : 0u);
+                    if (ks > 1) umma_words<TF32>(d_tmem, a_lo + 2, kDescHi, b_first + 2, idesc, 1u);
+                    if (ks > 2) umma_words<TF32>(d_tmem, a_lo + 4, kDescHi, b_first + 4, idesc, 1u);
+                    if (ks > 3) umma_words<TF32>(d_tmem, a_lo + 6, kDescHi, b_first + 6, idesc, 1u);
                 } else if constexpr (MODE == 1) {
 #pragma unroll
                     for (int ky = 0; ky < KH; ky++) {
                         const uint32_t a_t = a_lo + uint32_t(ky * 128);           // next image row of the box: 16 px * 128 B
                         const uint32_t b_t = b_first + uint32_t(ky) * b_ky_step;
-                        umma_f16_words(d_tmem, a_t, b_t, idesc, (it | ky) != 0 ? 1u : 0u);
-                        if (ks > 1) umma_f16_words(d_tmem, a_t + 2, b_t + 2, idesc, 1u);
-                        if (ks > 2) umma_f16_words(d_tmem, a_t + 4, b_t + 4, idesc, 1u);
-                        if (ks > 3) umma_f16_words(d_tmem, a_t + 6, b_t + 6, idesc, 1u);
+                        umma_words<TF32>(d_tmem, a_t, kDescHi, b_t, idesc, (it | ky) != 0 ? 1u : 0u);
+                        if (ks > 1) umma_words<TF32>(d_tmem, a_t + 2, kDescHi, b_t + 2, idesc, 1u);
+                        if (ks > 2) umma_words<TF32>(d_tmem, a_t + 4, kDescHi, b_t + 4, idesc, 1u);
+                        if (ks > 3) umma_words<TF32>(d_tmem, a_t + 6, kDescHi, b_t + 6, idesc, 1u);
                     }
                 } else {
 #pragma unroll
@@ -447,10 +499,10 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
                         for (int kx = 0; kx < KW; kx++) {
                             const uint32_t a_t = a_lo + (uint32_t(ky) * bw + uint32_t(kx)) * 8u;   // pixel rows of 128 B
                             const uint32_t b_t = b_first + uint32_t(ky * KW + kx) * b_tap_step;
-                            umma_f16_words2(d_tmem, a_t, halo_hi, b_t, idesc, (it | ky | kx) != 0 ? 1u : 0u);
-                            if (ks > 1) umma_f16_words2(d_tmem, a_t + 2, halo_hi, b_t + 2, idesc, 1u);
-                            if (ks > 2) umma_f16_words2(d_tmem, a_t + 4, halo_hi, b_t + 4, idesc, 1u);
-                            if (ks > 3) umma_f16_words2(d_tmem, a_t + 6, halo_hi, b_t + 6, idesc, 1u);
+                            umma_words<TF32>(d_tmem, a_t, halo_hi, b_t, idesc, (it | ky | kx) != 0 ? 1u : 0u);
+                            if (ks > 1) umma_words<TF32>(d_tmem, a_t + 2, halo_hi, b_t + 2, idesc, 1u);
+                            if (ks > 2) umma_words<TF32>(d_tmem, a_t + 4, halo_hi, b_t + 4, idesc, 1u);
+                            if (ks > 3) umma_words<TF32>(d_tmem, a_t + 6, halo_hi, b_t + 6, idesc, 1u);
                         }
                 }
                 umma_commit(&empty[stage]);                            // smem slot is free once these MMAs have read it
@@ -537,7 +589,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_expect_tx(b_full, uint32_t(p.b_total));
                 for (int tp = 0; tp < taps; tp++)
                     for (int kb = 0; kb < p.num_kb; kb++)
-                        tma_load_2d(bres + size_t(tp * p.num_kb + kb) * p.n_chunk * 128, &map_b, b_full, tp * p.k_pad + kb * BLOCK_K, 0);
+                        tma_load_2d(bres + size_t(tp * p.num_kb + kb) * p.n_chunk * 128, &map_b, b_full, tp * p.k_pad + kb * p.kb_elems, 0);
             }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
@@ -555,24 +607,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_expect_tx(&full[stage], uint32_t(p.a_tx + b_bytes));
                     uint8_t* a_dst = smem + size_t(stage) * stage_bytes;
                     if (p.halo) {
-                        tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 - p.pw, y0 - p.ph, img);
+                        tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 - p.pw, y0 - p.ph, img);
                         for (int tp = 0; tp < taps && !p.b_resident; tp++)
-                            tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * BLOCK_K,
+                            tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * p.kb_elems,
                                         n_idx * p.n_chunk);
                     } else if (p.rowbox) {
-                        tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 + tap - p.pw, y0 - p.ph, img);
+                        tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 + tap - p.pw, y0 - p.ph, img);
                         for (int ky = 0; ky < p.kh && !p.b_resident; ky++)
                             tma_load_2d(a_dst + p.a_bytes + ky * p.n_chunk * 128, &map_b, &full[stage],
-                                        (ky * p.kw + tap) * p.k_pad + kb * BLOCK_K, n_idx * p.n_chunk);
+                                        (ky * p.kw + tap) * p.k_pad + kb * p.kb_elems, n_idx * p.n_chunk);
                     } else {
                         if (p.spatial) {
                             const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                            tma_load_4d(a_dst, &map_a, &full[stage], kb * BLOCK_K, x0 + kx - p.pw, y0 + ky - p.ph, img);
+                            tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 + kx - p.pw, y0 + ky - p.ph, img);
                         } else {
-                            tma_load_2d(a_dst, &map_a, &full[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+                            tma_load_2d(a_dst, &map_a, &full[stage], kb * p.kb_elems, m_tile * BLOCK_M);
                         }
                         if (!p.b_resident)
-                            tma_load_2d(a_dst + p.a_bytes, &map_b, &full[stage], tap * p.k_pad + kb * BLOCK_K, n_idx * p.n_chunk);
+                            tma_load_2d(a_dst + p.a_bytes, &map_b, &full[stage], tap * p.k_pad + kb * p.kb_elems, n_idx * p.n_chunk);
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -586,15 +638,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem)), bres_lo = umma_desc_lo(smem_u32(bres));
         const uint32_t stage16 = uint32_t(stage_bytes >> 4);
+#define VSE_MMA(M, A, B)                                                                                                      \
+    do {                                                                                                                      \
+        if (p.tf32) mma_warp_loop<M, A, B, true>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);  \
+        else mma_warp_loop<M, A, B, false>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);       \
+    } while (0)
         if (p.halo) {
-            if (p.kh == 3 && p.kw == 3) mma_warp_loop<2, 3, 3>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
-            else mma_warp_loop<2, 0, 0>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
+            if (p.kh == 3 && p.kw == 3) VSE_MMA(2, 3, 3);
+            else VSE_MMA(2, 0, 0);
         } else if (p.rowbox) {
-            if (p.kh == 3) mma_warp_loop<1, 3, 0>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
-            else mma_warp_loop<1, 0, 0>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
+            if (p.kh == 3) VSE_MMA(1, 3, 0);
+            else VSE_MMA(1, 0, 0);
         } else {
-            mma_warp_loop<0, 1, 1>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);
+            VSE_MMA(0, 1, 1);
         }
+#undef VSE_MMA
     } else {
         // ---------------- epilogue: warps 2..9 ----------------
         const int q = warp & 3, half = (warp - 2) >> 2;
@@ -616,22 +674,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 
-TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps) {
+TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, bool tf32) {
     TcWeights t;
+    t.tf32 = tf32 ? 1 : 0;
+    const int kb = tf32 ? 32 : BLOCK_K;            // elements per 128-byte K row
     const int n_mma = round_up_i(cout, 16);
     t.n_chunks = (n_mma + 255) / 256;
     t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, t.n_chunks > 1 ? 64 : 16);   // store boxes are 64 columns wide
-    t.k_pad = round_up_i(cin, BLOCK_K);
+    t.k_pad = round_up_i(cin, kb);
     t.taps = taps;
     const size_t rows = size_t(t.n_chunks) * t.n_chunk, cols = size_t(taps) * t.k_pad;
-    t.b.assign(rows * cols, 0);
+    const int wpe = tf32 ? 2 : 1;                  // 16-bit words per element
+    t.b.assign(rows * cols * wpe, 0);
     for (int co = 0; co < cout; co++)
         for (int tp = 0; tp < taps; tp++)
             for (int ci = 0; ci < cin; ci++) {
-                __half h = __float2half_rn(w[(size_t(co) * taps + tp) * cin + ci]);
-                uint16_t bits;
-                std::memcpy(&bits, &h, 2);
-                t.b[size_t(co) * cols + size_t(tp) * t.k_pad + ci] = bits;
+                const float f = w[(size_t(co) * taps + tp) * cin + ci];
+                const size_t at = size_t(co) * cols + size_t(tp) * t.k_pad + ci;
+                if (tf32) {
+                    std::memcpy(&t.b[at * 2], &f, 4);
+                } else {
+                    __half h = __float2half_rn(f);
+                    std::memcpy(&t.b[at], &h, 2);
+                }
             }
     return t;
 }
@@ -675,7 +740,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                          const cuuint32_t* box) {
+                          const cuuint32_t* box, bool f32 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return "cuTensorMapEncodeTiled unavailable";
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -687,7 +752,7 @@ static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t
     }
     const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                     : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), base, dims, strides_bytes, box, estr,
+    CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), base, dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")";
     return "";
@@ -696,14 +761,18 @@ static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t
 std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
                           int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox, bool allow_halo) {
     t.valid = false;
-    if ((reinterpret_cast<uintptr_t>(in) & 15) || (in_cs & 7)) return "activation view not 16-byte aligned";
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (!w.tf32 && (in_cs & 7))) return "activation view not 16-byte aligned";
     if (pixels <= 0) return "empty";
     t.kh = kh; t.kw = kw; t.ph = ph; t.pw = pw;
     t.k_pad = w.k_pad;
     t.cin = cin;
     t.rowbox = 0;
     t.halo = 0;
-    t.num_kb = (cin + BLOCK_K - 1) / BLOCK_K;
+    t.tf32 = w.tf32;
+    const int es = w.tf32 ? 4 : 2;               // activation / weight element size
+    const cuuint32_t kbe = cuuint32_t(128 / es);   // elements per 128-byte K row (64 halves or 32 floats)
+    if (w.tf32 && (in_cs & 3)) return "fp32 activation view not 16-byte aligned";
+    t.num_kb = (cin + int(kbe) - 1) / int(kbe);
     t.n_chunk = w.n_chunk;
     t.n_chunks = w.n_chunks;
     // weights resident in shared memory when the whole (single-chunk) matrix is small: tiles then stream activations only
@@ -715,9 +784,9 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         t.M = int(pixels);
         t.num_m_tiles = int((pixels + BLOCK_M - 1) / BLOCK_M);
         cuuint64_t dims[2] = {cuuint64_t(cin), cuuint64_t(pixels)};
-        cuuint64_t strides[1] = {cuuint64_t(in_cs) * 2};
-        cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
-        err = encode(&t.map_a, const_cast<void*>(in), 2, dims, strides, box);
+        cuuint64_t strides[1] = {cuuint64_t(in_cs) * es};
+        cuuint32_t box[2] = {kbe, BLOCK_M};
+        err = encode(&t.map_a, const_cast<void*>(in), 2, dims, strides, box, w.tf32);
     } else {
         t.spatial = 1;
         t.n_img = n_img; t.H = H; t.W = W;
@@ -730,21 +799,21 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         t.tiles_y = t.halo ? (H + 15) / 16 : (H + 7) / 8;
         t.num_m_tiles = n_img * t.tiles_x * t.tiles_y;
         cuuint64_t dims[4] = {cuuint64_t(cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(n_img)};
-        cuuint64_t strides[3] = {cuuint64_t(in_cs) * 2, cuuint64_t(W) * in_cs * 2, cuuint64_t(H) * W * in_cs * 2};
+        cuuint64_t strides[3] = {cuuint64_t(in_cs) * es, cuuint64_t(W) * in_cs * es, cuuint64_t(H) * W * in_cs * es};
         // rowbox: one box of 8 + kh - 1 rows per (kx, k-block) instead of one 8-row box per tap — kh x less L2->smem
         // traffic for the activations.  Needs >= 3 pipeline stages of (box + kh weight slices) in shared memory.
         const int a_box = (8 + kh - 1) * 16 * 128;
         const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + kh * w.n_chunk * 128);
         t.rowbox = (!t.halo && allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - 16384 - kOutBufs * kOutBufBytes) ? 1 : 0;
-        cuuint32_t box[4] = {BLOCK_K, cuuint32_t(t.halo ? 8 + kw - 1 : 16), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + kh - 1 : 8), 1};
-        err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box);
+        cuuint32_t box[4] = {kbe, cuuint32_t(t.halo ? 8 + kw - 1 : 16), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + kh - 1 : 8), 1};
+        err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box, w.tf32);
     }
     if (!err.empty()) return err;
     {
         cuuint64_t dims[2] = {cuuint64_t(w.taps) * w.k_pad, cuuint64_t(w.n_chunks) * w.n_chunk};
-        cuuint64_t strides[1] = {cuuint64_t(w.taps) * w.k_pad * 2};
-        cuuint32_t box[2] = {BLOCK_K, cuuint32_t(w.n_chunk)};
-        err = encode(&t.map_b, const_cast<void*>(wdev), 2, dims, strides, box);
+        cuuint64_t strides[1] = {cuuint64_t(w.taps) * w.k_pad * es};
+        cuuint32_t box[2] = {kbe, cuuint32_t(w.n_chunk)};
+        err = encode(&t.map_b, const_cast<void*>(wdev), 2, dims, strides, box, w.tf32);
         if (!err.empty()) return err;
     }
     t.valid = true;
@@ -755,23 +824,25 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
 static std::string tc_output_map(TcConv& t) {
     if (t.map_o_ptr == t.out && t.map_o_cs == t.out_cs && t.map_o_n == t.n_store) return "";
     std::string err;
+    const int es = t.tf32 ? 4 : 2;
+    const cuuint32_t cols = cuuint32_t(128 / es);   // one staging row = 64 fp16 or 32 fp32 columns
     if (t.spatial) {
         cuuint64_t dims[4] = {cuuint64_t(t.n_store), cuuint64_t(t.W), cuuint64_t(t.H), cuuint64_t(t.n_img)};
-        cuuint64_t strides[3] = {cuuint64_t(t.out_cs) * 2, cuuint64_t(t.W) * t.out_cs * 2, cuuint64_t(t.H) * t.W * t.out_cs * 2};
-        cuuint32_t box[4] = {BLOCK_K, cuuint32_t(t.halo ? 8 : 16), cuuint32_t(t.halo ? 16 : 8), 1};
-        err = encode(&t.map_o, t.out, 4, dims, strides, box);
+        cuuint64_t strides[3] = {cuuint64_t(t.out_cs) * es, cuuint64_t(t.W) * t.out_cs * es, cuuint64_t(t.H) * t.W * t.out_cs * es};
+        cuuint32_t box[4] = {cols, cuuint32_t(t.halo ? 8 : 16), cuuint32_t(t.halo ? 16 : 8), 1};
+        err = encode(&t.map_o, t.out, 4, dims, strides, box, t.tf32);
     } else {
         cuuint64_t dims[2] = {cuuint64_t(t.n_store), cuuint64_t(t.M)};
-        cuuint64_t strides[1] = {cuuint64_t(t.out_cs) * 2};
-        cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
-        err = encode(&t.map_o, t.out, 2, dims, strides, box);
+        cuuint64_t strides[1] = {cuuint64_t(t.out_cs) * es};
+        cuuint32_t box[2] = {cols, BLOCK_M};
+        err = encode(&t.map_o, t.out, 2, dims, strides, box, t.tf32);
     }
     if (err.empty()) { t.map_o_ptr = t.out; t.map_o_cs = t.out_cs; t.map_o_n = t.n_store; }
     return err;
 }
 
 std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
-    if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & 7)) return "output view not 16-byte aligned";
+    if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (t.tf32 ? 3 : 7))) return "output view not 16-byte aligned";
     {
         std::string err = tc_output_map(t);
         if (!err.empty()) return err;
@@ -781,6 +852,8 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     p.kh = t.kh; p.kw = t.kw; p.ph = t.ph; p.pw = t.pw; p.num_kb = t.num_kb; p.k_pad = t.k_pad;
     p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = t.num_m_tiles;
     p.cin = t.cin;
+    p.tf32 = t.tf32;
+    p.kb_elems = t.tf32 ? 32 : BLOCK_K;
     p.rowbox = t.rowbox;
     p.halo = t.halo;
     p.a_tx = t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh - 1) * 16 * 128 : A_BYTES;

@@ -17,11 +17,12 @@ struct TcWeights {          // built once per plan step (host), uploaded as fp16
     int n_chunks = 0;       // output-channel chunks (tiles along N)
     int k_pad = 0;          // per-tap K extent in the B matrix (multiple of 64)
     int taps = 1;
-    std::vector<uint16_t> b;  // fp16 bits, [n_chunks * n_chunk][taps * k_pad], K-major, zero padded
+    int tf32 = 0;           // 1: fp32 elements (tcgen05 kind::tf32), k_pad a multiple of 32; 0: fp16, multiple of 64
+    std::vector<uint16_t> b;  // raw 16-bit words: fp16 bits (or 2 words per fp32), [n_chunks * n_chunk][taps * k_pad], K-major, zero padded
 };
 
 // cout / cin: real channel counts; weights fp32 [cout][kh*kw][cin]
-TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps);
+TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, bool tf32 = false);
 
 // Pixel-packed 1x1 conv: `pack` consecutive pixels (channel stride in_cs, pack * in_cs == 64) form ONE GEMM row of K = 64
 // and the weights become block-diagonal [pack * out_cs][64]: row g*out_cs + co, column g*in_cs + ci = w[co][ci].  The
@@ -41,6 +42,7 @@ struct TcConv {
     int kh = 1, kw = 1, ph = 0, pw = 0;
     int cin = 0;            // real input channels (the MMA loop skips the all-zero tail of the last K block)
     int rowbox = 0;         // KxK: A boxes span 8 + kh - 1 image rows and serve all vertical taps (see gemm_tc.cu)
+    int tf32 = 0;           // fp32 activations / weights through kind::tf32 MMAs, fp32 output
     int pack = 0;           // >0: pixel-packed flat conv (rows of `pack` pixels)
     int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
     int halo = 0;           // KxK: one (16 + kh - 1) x (8 + kw - 1) box per k-block serves every tap (see gemm_tc.cu)

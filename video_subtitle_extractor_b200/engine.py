@@ -17,12 +17,12 @@ _lib = None
 
 PLAN_DET, PLAN_REC = 0, 1
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
-PRECISION_FP16, PRECISION_FP32 = 0, 1
+PRECISION_FP16, PRECISION_FP32, PRECISION_TF32 = 0, 1, 2
 FLAG_NO_TENSOR_CORES = 1
 FLAG_NO_FAST_KERNELS = 2
 FLAG_NO_FUSED_HEAD, FLAG_NO_SE_FUSION, FLAG_NO_ROWBOX, FLAG_NO_FAST_DW, FLAG_NO_FAST_STEM, FLAG_NO_PIXEL_PACK = 4, 8, 16, 32, 64, 128
 FLAG_NO_CONCAT_GATHER, FLAG_NO_HALO = 256, 512
-FLAG_DET_FP32 = 1024
+FLAG_DET_FP32, FLAG_DET_TF32 = 1024, 2048
 
 
 class VseConfig(C.Structure):
