@@ -378,7 +378,7 @@ def run_b200(args, rank, local_rank, world):
                        "frames_per_step_per_gpu": B, "global_frames_per_step": world * B, "frame": [H, W, 3],
                        "parallelism": f"frame-range sharding x{world}", "text_lines_per_step": n_lines / max(args.steps, 1),
                        "l2": f"inputs larger than L2: {args.pool} distinct batches x {B * frame_bytes / 1e6:.0f} MB cycled",
-                       "precision": "fp16 activations, fp32 accumulate"},
+                       "precision": "fp16 activations, fp32 accumulate" + (f"; vse_config.flags={args.flags}" if args.flags else "")},
             "device_ms_per_step": dev_s / args.steps * 1e3, "stage_ms_last_e2e_step": stage_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_max / args.steps * 1e3, "device_ms_per_step": dev_s_e2e / args.steps * 1e3,
