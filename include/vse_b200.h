@@ -55,7 +55,7 @@ enum {
     /* finer A/B switches (bisecting numerical differences); each disables one specialised path */
     VSE_FLAG_NO_FUSED_HEAD = 4, VSE_FLAG_NO_SE_FUSION = 8, VSE_FLAG_NO_ROWBOX = 16, VSE_FLAG_NO_FAST_DW = 32,
     VSE_FLAG_NO_FAST_STEM = 64, VSE_FLAG_NO_PIXEL_PACK = 128,
-    VSE_FLAG_NO_CONCAT_GATHER = 256, VSE_FLAG_NO_HALO = 512,
+    VSE_FLAG_NO_CONCAT_GATHER = 256, VSE_FLAG_NO_HALO = 512, VSE_FLAG_NO_SE_CONV = 4096,
     /* not an A/B switch: run the DETECTOR plan with fp32 activations whatever vse_config.precision says (V4/ch_det, the
      * accurate-mode detector of backend/tools/paddle_model_config.py:60,70, exceeds the fp16 range) */
     VSE_FLAG_DET_FP32 = 1024,

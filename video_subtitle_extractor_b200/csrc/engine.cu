@@ -435,10 +435,51 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         return size_t(cx.geos[g].total) * value_cs(pd, v) * elt_size(which, r);
     };
     const int nsteps = int(pd.steps.size());
+    // Fused residual squeeze-excite around a 1x1 convolution (RSE in-convs of the FPN): conv(act none) -> GPOOL -> FC -> FC
+    // -> CHSCALE(residual).  mean(conv(x)) = W mean(x) + b, so the gate is computed from the conv's INPUT and applied in the
+    // conv's epilogue: the conv output is never pooled nor re-read.  The group's results (gate vector, CHSCALE output) are
+    // then produced at the conv's step, so their arena lifetime starts there.
+    std::vector<int> fd(pd.values.size());
+    for (size_t v = 0; v < pd.values.size(); v++) fd[v] = pd.values[v].first_def;
+    cx.se_conv.assign(pd.steps.size(), 0);
+    if (!keep_all && plan_prec_[which] == VSE_PRECISION_FP16 &&
+        !(cfg.flags & (VSE_FLAG_NO_FAST_KERNELS | VSE_FLAG_NO_TENSOR_CORES | VSE_FLAG_NO_SE_CONV))) {
+        auto readers = [&](int vid) {
+            int n = 0;
+            for (const StepRec& q : pd.steps)
+                for (int i = 0; i < 4; i++) n += q.ins[i] == vid;
+            return n;
+        };
+        auto plain = [](const StepRec& f) { return !f.p[P_HAS_POST] && !f.p[P_HAS_RES] && f.p[P_ACT2] == ACT_NONE; };
+        for (int k = 0; k + 4 < nsteps; k++) {
+            const StepRec& c = pd.steps[k];
+            const StepRec &gp = pd.steps[k + 1], &f1 = pd.steps[k + 2], &f2 = pd.steps[k + 3], &ch = pd.steps[k + 4];
+            if (c.op != OP_CONV || gp.op != OP_GPOOL || f1.op != OP_VECLIN || f2.op != OP_VECLIN || ch.op != OP_CHSCALE) continue;
+            if (c.p[P_KH] != 1 || c.p[P_KW] != 1 || c.p[P_SH] != 1 || c.p[P_SW] != 1 || c.p[P_PH] || c.p[P_PW]) continue;
+            if (c.p[P_ACT] != ACT_NONE || !plain(c) || !plain(f1) || !plain(f2) || lp.tcw[k].n_chunk == 0) continue;
+            if (gp.ins[0] != c.out || f1.ins[0] != gp.out || f2.ins[0] != f1.out || ch.ins[0] != c.out || ch.ins[1] != f2.out) continue;
+            if (!ch.p[P_RESIDUAL] || c.ins[0] == pd.hdr.input_vid) continue;
+            const ValueRec &vc = pd.values[c.out], &vo = pd.values[ch.out];
+            if (vc.alias_of >= 0 || vo.alias_of >= 0 || vc.dtype != DT_ACT || vo.dtype != DT_ACT) continue;
+            const int cout = c.p[P_COUT];
+            if (cout % 16 || f1.p[P_CIN] != cout || f2.p[P_COUT] != cout || f2.p[P_CIN] != f1.p[P_COUT] || f1.p[P_COUT] > 512 ||
+                c.p[P_CIN] > 2048 || vo.channels != cout)
+                continue;
+            if (readers(c.out) != 2 || readers(gp.out) != 1 || readers(f1.out) != 1 || readers(f2.out) != 1) continue;
+            const Geo& g = cx.geos[cx.vals[c.out].geo];
+            bool uniform = true;
+            for (auto& t : g.tab) uniform = uniform && t.h == g.tab[0].h && t.w == g.tab[0].w;
+            if (!uniform || !lp.dev[k + 2].w_t || !lp.dev[k + 3].w_t || !lp.dev[k + 2].bias || !lp.dev[k + 3].bias || !lp.dev[k].bias) continue;
+            cx.se_conv[k] = 1;
+            scratch = std::max(scratch, size_t(cx.n_img) * 64 * pad8(c.p[P_CIN]) * sizeof(float));   // partial sums of the conv input
+            fd[f2.out] = k;
+            fd[ch.out] = k;
+        }
+    }
     for (int k = -1; k <= nsteps; k++) {
         for (size_t v = 0; v < pd.values.size(); v++) {
             const ValueRec& r = pd.values[v];
-            if (r.alias_of >= 0 || r.first_def != k || r.first_def == -2) continue;
+            if (r.alias_of >= 0 || fd[v] != k || r.first_def == -2) continue;
             if (int(v) == pd.hdr.input_vid) continue;  // the input lives in caller memory
             ValueRt& rt = cx.vals[v];
             rt.bytes = root_bytes(int(v));
@@ -668,6 +709,35 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                     }
                 } else if (s.op == OP_STEM && fast && !(cfg.flags & VSE_FLAG_NO_FAST_STEM) && launch_stem_fast(a, s.p[P_COUT], max_units(2), stream)) {
                     cx.kind[k] = 2;
+                } else if (s.op == OP_CONV && cx.se_conv[k] && cx.tc[k].valid) {
+                    // fused residual squeeze-excite (see build_context): pool the conv INPUT, gate from W mean(x) + b, conv
+                    // epilogue applies y + y * gate and writes the CHSCALE output
+                    const StepRec &f1 = pd.steps[k + 2], &f2 = pd.steps[k + 3], &chs = pd.steps[k + 4];
+                    const int cin = s.p[P_CIN], cout = s.p[P_COUT], cxp = pad8(cin);
+                    const Geo& gx = geo_of(s.ins[0]);
+                    int splits = std::max(1, std::min({64, gx.max_pix / 64, std::max((4 * sm_count + cx.n_img - 1) / std::max(cx.n_img, 1), gx.max_pix / 1024)}));
+                    float* partial = reinterpret_cast<float*>(static_cast<char*>(arena_[which].p) + cx.scratch_off);
+                    if (size_t(cx.n_img) * splits * cxp * sizeof(float) > cx.scratch_bytes) throw StateError{"squeeze-excite scratch too small"};
+                    launch_gpool_partial(a.in, a.in_cs, cxp, a.tin, cx.n_img, partial, splits, prec, stream);
+                    float* gate = static_cast<float*>(ptr_of(f2.out));
+                    launch_se_gate(partial, splits, cxp, cout, f1.p[P_COUT], a.tin, lp.dev[k + 2].w_t, lp.dev[k + 2].bias, f1.p[P_ACT],
+                                   f1.f[F_HS_SLOPE], f1.f[F_HS_OFFSET], lp.dev[k + 3].w_t, lp.dev[k + 3].bias, f2.p[P_ACT],
+                                   f2.f[F_HS_SLOPE], f2.f[F_HS_OFFSET], gate, cx.n_img, stream, d.w, d.bias, cin, cxp, d.w_co);
+                    a.out = ptr_of(chs.out);
+                    a.out_cs = value_cs(pd, chs.out);
+                    a.epi.gate = gate;
+                    a.epi.gate_c = cout;
+                    const int pack = std::max(cx.tc[k].pack, 1);
+                    a.epi.gate_rows = gx.max_pix / pack;
+                    if (gx.max_pix % pack) throw StateError{"squeeze-excite fusion: image size not a multiple of the pixel pack"};
+                    if (!launch_conv(which, int(k), a, prec)) throw StateError{"squeeze-excite fusion lost its tensor-core plan"};
+                    launches += 2;
+                    cx.kind[k] = 1;
+                    for (int j = 0; j < 4; j++) {
+                        k++;
+                        cx.kind[k] = 3;
+                        if (step_events) cudaEventRecord((*step_events)[k], stream);
+                    }
                 } else {
                     if (out_f32) a.cout_store = s.p[P_COUT];
                     if (launch_conv(which, int(k), a, prec)) cx.kind[k] = 1;

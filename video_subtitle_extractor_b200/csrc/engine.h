@@ -133,6 +133,7 @@ struct ExecContext {
     size_t scratch_off = 0, scratch_bytes = 0;
     int n_img = 0;
     std::vector<TcConv> tc;   // per step; valid => the step runs on the tcgen05 kernel for this geometry
+    std::vector<char> se_conv; // per step: 1 = 1x1 conv heading a fused residual squeeze-excite group (build_context)
     std::vector<int> kind;    // per step, filled by exec_steps: which kernel family ran (see Engine::time_steps)
 };
 

@@ -295,10 +295,9 @@ bool launch_dwconv_tiled(const ConvArgs& a, int max_out_h, int max_out_w, cudaSt
             a.tin, a.tout, a.in_cs, a.out_cs, a.cin_pad / 8, a.cin_pad, a.ph, a.pw};
     if (!d.bias) return false;
     const int key = a.kh * 100 + a.sh * 10 + a.sw;
-    static const bool dw_th4 = [] { const char* e = getenv("VSE_DW_TH4"); return e && atoi(e) != 0; }();   // tuning knob
     // channel block per CTA: 8 vectors (64 channels, 128 B per pixel), 4 for 32-channel layers, 2 for 16/24 channels
 #define VSE_DW_TILE(KK, SHH, SWW, THW, THN)                                                                              \
-    (d.cvecs >= 5   ? ((max_out_h <= 4 || dw_th4) ? dw_tile_launch<KK, SHH, SWW, 4, 8>(d, a, max_out_h, max_out_w, st)               \
+    (d.cvecs >= 5   ? (max_out_h <= 4 ? dw_tile_launch<KK, SHH, SWW, 4, 8>(d, a, max_out_h, max_out_w, st)               \
                                       : dw_tile_launch<KK, SHH, SWW, THW, 8>(d, a, max_out_h, max_out_w, st))            \
      : d.cvecs == 4 ? dw_tile_launch<KK, SHH, SWW, THN, 4>(d, a, max_out_h, max_out_w, st)                               \
                     : dw_tile_launch<KK, SHH, SWW, THN, 2>(d, a, max_out_h, max_out_w, st))
@@ -497,6 +496,9 @@ struct SeDev {
     const float* w1; const float* b1; const float* w2; const float* b2;
     int act1, act2; float slope1, offset1, slope2, offset2;
     float* out;
+    // optional pre-stage: the pooled tensor is y = W x + b of a 1x1 convolution, pooled from its INPUT x
+    // (mean(y) = W mean(x) + b): partial holds sums of x (cx channels, cx_pad stride), pre_w is [cx][pre_ld] (co contiguous)
+    const float* pre_w; const float* pre_b; int cx, cx_pad, pre_ld;
 };
 
 __device__ __forceinline__ float act_rt(float x, int act, float slope, float offset) {
@@ -511,8 +513,33 @@ __device__ __forceinline__ float act_rt(float x, int act, float slope, float off
     }
 }
 
-// w1t: [c][cm] (input-major), w2t: [cm][c]: consecutive threads own consecutive outputs, so weight reads are coalesced
-// and no warp shuffles sit on the critical path (these matrices are read once per image by a single CTA).
+// One small fully-connected layer inside a CTA: out[co] = act(bias[co] + sum_i w[i * ld + co] * in[i]).  The weights are
+// input-major (consecutive threads own consecutive outputs: coalesced reads, no shuffles) and the K range is split over
+// blockDim / n_out thread groups whose partial sums meet in shared memory.  in / part live in shared memory.
+__device__ __forceinline__ void cta_fc(const float* in, int n_in, const float* __restrict__ w, int ld, const float* __restrict__ bias,
+                                       int n_out, float* part, float* out, int act, float slope, float offset) {
+    const int nt = blockDim.x;
+    const int groups = n_out >= nt ? 1 : nt / n_out;
+    for (int co0 = 0; co0 < n_out; co0 += nt) {          // n_out > blockDim: several passes (groups == 1)
+        const int co = co0 + int(threadIdx.x) % (n_out >= nt ? nt : n_out), g = n_out >= nt ? 0 : int(threadIdx.x) / n_out;
+        float s = 0.f;
+        if (g < groups && co < n_out) {
+            const int chunk = (n_in + groups - 1) / groups;
+            const int i0 = g * chunk, i1 = min(n_in, i0 + chunk);
+#pragma unroll 8
+            for (int i = i0; i < i1; i++) s = fmaf(__ldg(w + size_t(i) * ld + co), in[i], s);
+        }
+        part[threadIdx.x] = s;
+        __syncthreads();
+        if (g == 0 && co < n_out) {
+            float t = bias[co];
+            for (int q = 0; q < groups; q++) t += part[q * n_out + (co - co0)];
+            out[co] = act_rt(t, act, slope, offset);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(512) se_gate_kernel(SeDev p) {
     extern __shared__ float sm[];
     float* mean = sm;                 // [c]
@@ -520,46 +547,35 @@ __global__ void __launch_bounds__(512) se_gate_kernel(SeDev p) {
     float* part = hid + p.cm;         // [blockDim.x]
     const int img = blockIdx.x;
     const float inv = 1.f / float(p.tin[img].h * p.tin[img].w);
-    for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < p.splits; k++) s += p.partial[(size_t(img) * p.splits + k) * p.c_pad + c];
-        mean[c] = s * inv;
-    }
-    __syncthreads();
-    // FC1: cm outputs, K = c split over blockDim / cm thread groups
-    const int groups = max(1, int(blockDim.x) / p.cm);
-    {
-        const int co = threadIdx.x % p.cm, g = threadIdx.x / p.cm;
-        float s = 0.f;
-        if (g < groups) {
-            const int chunk = (p.c + groups - 1) / groups;
-            const int i0 = g * chunk, i1 = min(p.c, i0 + chunk);
-#pragma unroll 4
-            for (int i = i0; i < i1; i++) s = fmaf(p.w1[size_t(i) * p.cm + co], mean[i], s);
+    if (p.pre_w) {
+        float* mean_x = part + blockDim.x;    // [cx]
+        for (int c = threadIdx.x; c < p.cx; c += blockDim.x) {
+            float s = 0.f;
+            for (int k = 0; k < p.splits; k++) s += p.partial[(size_t(img) * p.splits + k) * p.cx_pad + c];
+            mean_x[c] = s * inv;
         }
-        part[threadIdx.x] = s;
+        __syncthreads();
+        cta_fc(mean_x, p.cx, p.pre_w, p.pre_ld, p.pre_b, p.c, part, mean, ACT_NONE, 0.f, 0.f);   // mean(W x + b) = W mean(x) + b
+    } else {
+        for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
+            float s = 0.f;
+            for (int k = 0; k < p.splits; k++) s += p.partial[(size_t(img) * p.splits + k) * p.c_pad + c];
+            mean[c] = s * inv;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int co = threadIdx.x; co < p.cm; co += blockDim.x) {
-        float s = p.b1[co];
-        for (int g = 0; g < groups; g++) s += part[g * p.cm + co];
-        hid[co] = act_rt(s, p.act1, p.slope1, p.offset1);
-    }
-    __syncthreads();
-    for (int co = threadIdx.x; co < p.c; co += blockDim.x) {
-        float s = p.b2[co];
-#pragma unroll 4
-        for (int i = 0; i < p.cm; i++) s = fmaf(p.w2[size_t(i) * p.c + co], hid[i], s);
-        p.out[size_t(img) * p.c + co] = act_rt(s, p.act2, p.slope2, p.offset2);
-    }
+    cta_fc(mean, p.c, p.w1, p.cm, p.b1, p.cm, part, hid, p.act1, p.slope1, p.offset1);
+    cta_fc(hid, p.cm, p.w2, p.c, p.b2, p.c, part, p.out + size_t(img) * p.c, p.act2, p.slope2, p.offset2);
 }
 
 void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, const ImgTab* tin, const float* w1,
                     const float* b1, int act1, float slope1, float offset1, const float* w2, const float* b2, int act2,
-                    float slope2, float offset2, float* out, int n_img, cudaStream_t st) {
-    SeDev d{partial, splits, c_pad, c, cm, tin, w1, b1, w2, b2, act1, act2, slope1, offset1, slope2, offset2, out};
+                    float slope2, float offset2, float* out, int n_img, cudaStream_t st, const float* pre_w, const float* pre_b,
+                    int cx, int cx_pad, int pre_ld) {
+    SeDev d{partial, splits, c_pad, c, cm, tin, w1, b1, w2, b2, act1, act2, slope1, offset1, slope2, offset2, out,
+            pre_w, pre_b, cx, cx_pad, pre_ld};
     const int threads = 512;   // cm <= threads is checked by the caller
-    se_gate_kernel<<<n_img, threads, size_t(c + cm + threads) * sizeof(float), st>>>(d);
+    se_gate_kernel<<<n_img, threads, size_t(c + cm + threads + (pre_w ? cx : 0)) * sizeof(float), st>>>(d);
 }
 
 // ------------------------------------------------------------------------------------------------

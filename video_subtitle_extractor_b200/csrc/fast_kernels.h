@@ -27,7 +27,8 @@ bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, con
 // w1 / w2 are the TRANSPOSED (input-major) matrices: w1[c][cm], w2[cm][c]; cm <= 512.
 void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, const ImgTab* tin, const float* w1,
                     const float* b1, int act1, float slope1, float offset1, const float* w2, const float* b2, int act2,
-                    float slope2, float offset2, float* out, int n_img, cudaStream_t st);
+                    float slope2, float offset2, float* out, int n_img, cudaStream_t st, const float* pre_w = nullptr,
+                    const float* pre_b = nullptr, int cx = 0, int cx_pad = 0, int pre_ld = 0);
 
 // one source of a concat gather: a channel slice of the output filled from `in` (nearest-upsampled by scale_px, and/or
 // multiplied by a per-image channel gate as CHSCALE does).  Sources must be ordered by ascending slice offset.

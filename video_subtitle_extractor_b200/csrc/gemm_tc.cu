@@ -46,6 +46,8 @@ struct TcParams {
     const void* res;
     int res_cs, act, act2;
     float hs_slope, hs_offset;
+    const float* gate;   // optional per-image channel gate (fused squeeze-excite): v += v * gate[row / gate_rows][channel]
+    int gate_c, gate_rows;
     int n_total;       // n_chunks * n_chunk (bias / post arrays are readable up to here)
     int param_smem;    // 1: bias/scale/shift staged in shared memory
 };
@@ -276,8 +278,9 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 // 16 accumulator columns of one output pixel -> 16 output values: fp16 (two 16-byte pieces) or fp32 (four pieces)
 template <int ACT, bool POST, bool OUTF32>
 __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* raw, const float* pb, const float* ps,
-                                            const float* pt, int cb, long long pix, uint4* out4) {
+                                            const float* pt, int cb, long long pix, uint4* out4, const float* grow) {
     float v[16];
+    const float* gp = grow ? grow + (cb % p.gate_c) : nullptr;
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
         const float4 b = ld4(pb + cb + 4 * j4);
@@ -288,6 +291,10 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* r
         if constexpr (POST) {
             const float4 sc = ld4(ps + cb + 4 * j4), sh = ld4(pt + cb + 4 * j4);
             x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y); x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
+        }
+        if (gp) {   // residual squeeze-excite: y + y * gate
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gp + 4 * j4));
+            x0 = fmaf(x0, g.x, x0); x1 = fmaf(x1, g.y, x1); x2 = fmaf(x2, g.z, x2); x3 = fmaf(x3, g.w, x3);
         }
         v[4 * j4 + 0] = x0; v[4 * j4 + 1] = x1; v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
     }
@@ -358,6 +365,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
             const long long m = (long long)m_tile * BLOCK_M + row;
             if (m < p.M) pix = m;
         }
+        const float* grow = (p.gate && pix >= 0) ? p.gate + size_t(pix / p.gate_rows) * p.gate_c : nullptr;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
@@ -373,7 +381,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                     tmem_ld16_nowait(taddr + uint32_t(c0), raw0);       // .sync.aligned: whole (converged) warp
                     tmem_ld_wait();
                     uint4 o[4];
-                    epi_chunk16<ACT, POST, true>(p, raw0, pb, ps, pt, ch0 + c0, pix, o);
+                    epi_chunk16<ACT, POST, true>(p, raw0, pb, ps, pt, ch0 + c0, pix, o, grow);
 #pragma unroll
                     for (int j = 0; j < 4; j++) st_shared_16(buf + uint32_t(((j0 + j) ^ (row & 7)) << 4), o[j]);
                 } else {
@@ -383,11 +391,11 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                     if (two) tmem_ld16_nowait(taddr + uint32_t(c0 + 16), raw1);
                     tmem_ld_wait();
                     uint4 o[2];
-                    epi_chunk16<ACT, POST, false>(p, raw0, pb, ps, pt, ch0 + c0, pix, o);
+                    epi_chunk16<ACT, POST, false>(p, raw0, pb, ps, pt, ch0 + c0, pix, o, grow);
                     st_shared_16(buf + uint32_t(((j0 + 0) ^ (row & 7)) << 4), o[0]);
                     st_shared_16(buf + uint32_t(((j0 + 1) ^ (row & 7)) << 4), o[1]);
                     if (two) {
-                        epi_chunk16<ACT, POST, false>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix, o);
+                        epi_chunk16<ACT, POST, false>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix, o, grow);
                         st_shared_16(buf + uint32_t(((j0 + 2) ^ (row & 7)) << 4), o[0]);
                         st_shared_16(buf + uint32_t(((j0 + 3) ^ (row & 7)) << 4), o[1]);
                     }
@@ -744,14 +752,7 @@ static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t
     EncodeTiledFn fn = encode_fn();
     if (!fn) return "cuTensorMapEncodeTiled unavailable";
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    static int promo = -1;   // tuning knob (profiling only): VSE_TC_L2PROMO = 0 none | 1 64B | 2 128B (default) | 3 256B
-    if (promo < 0) {
-        const char* e = getenv("VSE_TC_L2PROMO");
-        promo = e ? atoi(e) : 2;
-        if (promo < 0 || promo > 3) promo = 2;
-    }
-    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                    : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    const CUtensorMapL2promotion pr = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;   // 64B / 256B / none measured equal on these layers
     CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), base, dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")";
@@ -876,6 +877,7 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     p.bias = t.epi.bias; p.post_scale = t.epi.post_scale; p.post_shift = t.epi.post_shift;
     p.res = t.epi.res; p.res_cs = t.epi.res_cs; p.act = t.epi.act; p.act2 = t.epi.act2;
     p.hs_slope = t.epi.hs_slope; p.hs_offset = t.epi.hs_offset;
+    p.gate = t.epi.gate; p.gate_c = t.epi.gate_c; p.gate_rows = std::max(t.epi.gate_rows, 1);
     const size_t smem = size_t(p.stages) * stage_bytes + p.b_total + kOutBufs * kOutBufBytes + 1024 + kBarRegion + param_bytes;
     static bool configured[64] = {};   // per device: the attribute belongs to the device's copy of the kernel
     int dev = 0;

@@ -21,6 +21,10 @@ struct Epilogue {
     int res_cs = 0;
     int act = 0, act2 = 0;
     float hs_slope = 0.f, hs_offset = 0.f;
+    // tensor-core path only: per-image squeeze-excite gate applied as v += v * gate[img][channel] (fused RSE block)
+    const float* gate = nullptr;
+    int gate_c = 0;     // channels per image in `gate` (multiple of 16)
+    int gate_rows = 0;  // GEMM rows (pixels, or packed pixel groups) per image
 };
 
 struct ConvArgs {

@@ -23,6 +23,7 @@ FLAG_NO_FAST_KERNELS = 2
 FLAG_NO_FUSED_HEAD, FLAG_NO_SE_FUSION, FLAG_NO_ROWBOX, FLAG_NO_FAST_DW, FLAG_NO_FAST_STEM, FLAG_NO_PIXEL_PACK = 4, 8, 16, 32, 64, 128
 FLAG_NO_CONCAT_GATHER, FLAG_NO_HALO = 256, 512
 FLAG_DET_FP32, FLAG_DET_TF32 = 1024, 2048
+FLAG_NO_SE_CONV = 4096
 
 
 class VseConfig(C.Structure):
