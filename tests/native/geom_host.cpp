@@ -52,9 +52,10 @@ int gh_db_stage1(const int* xl, const int* xr, int rows, int y0, float* box8) {
     return ok ? 1 : 0;
 }
 
-// score mask rows: for the bbox-relative integer quad, row y -> [xa, xb] (returns 0 if the row is empty)
-int gh_quad_row_span(const int* qx, const int* qy, int y, int* xa, int* xb) {
-    return vse::dbpost::quad_row_span(qx, qy, y, xa, xb) ? 1 : 0;
+// score mask rows: for the window-relative integer quad and the (w x h) window, row y -> [xa, xb] clipped to the window
+// (returns 0 if the row is empty)
+int gh_quad_row_span(const int* qx, const int* qy, int w, int h, int y, int* xa, int* xb) {
+    return vse::dbpost::quad_row_span(qx, qy, w, h, y, xa, xb) ? 1 : 0;
 }
 
 void gh_score_window(const float* box8, int rw, int rh, int* win /*xmin,ymin,xmax,ymax*/, int* qx, int* qy) {

@@ -62,57 +62,120 @@ VSE_HD inline long long floor_div(long long a, long long b) {  // b > 0
     return (a % b != 0 && a < 0) ? q - 1 : q;
 }
 
-// Row `y` of cv::fillPoly(mask, quad) for a window-relative integer quad: the union of the scan-line fill
-// (16.16 fixed-point edges, rows [y0, y1)) and the 8-connected Bresenham boundary lines.  For a convex quad the union
-// on one row is a single interval [xa, xb] (not yet clipped to the window).
-VSE_HD inline bool quad_row_span(const int* qx, const int* qy, int y, int* xa, int* xb) {
+// cv::clipLine(Size(w, h), pt1, pt2) on 64-bit points (imgproc/drawing.cpp): Cohen-Sutherland with double-precision
+// intersections truncated toward zero.  Returns true when (part of) the segment is inside; the points are updated in place
+// exactly as OpenCV leaves them (also when the answer is false).
+VSE_HD inline bool cv_clip_line(long long w, long long h, long long& x1, long long& y1, long long& x2, long long& y2) {
+    if (w <= 0 || h <= 0) return false;
+    const long long right = w - 1, bottom = h - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// Row `y` of cv::fillPoly(mask(h x w), quad) for a window-relative integer quad whose corners may lie outside the
+// window (a text box cut by the map border) — bit for bit what OpenCV 4.13 draws (checked on 20 000 random quads,
+// tests/test_geom_cpu.py): per edge
+//   * the 8-connected boundary line is drawn between the cv::clipLine'd end points (cv::LineIterator, left to right,
+//     ties keep the minor coordinate) — clipping restarts the Bresenham walk;
+//   * the scan-line edge takes its x from the clipped end points ALWAYS and its y from them only when the clipped points
+//     differ in y; slope = truncated 16.16 quotient; start x extrapolated back to the unclipped top row;
+//   * a row is filled from ceil(x_left) to floor(x_right) (16.16), clamped to the window.
+// For a convex quad the union on one row is a single interval [xa, xb], already clipped to the window.
+VSE_HD inline bool quad_row_span(const int* qx, const int* qy, int w, int h, int y, int* xa, int* xb) {
+    if (y < 0 || y >= h) return false;
     bool any = false;
     long long lo = 0, hi = 0;
     auto add = [&](long long a, long long b) {
+        if (a < 0) a = 0;
+        if (b > w - 1) b = w - 1;
         if (a > b) return;
         if (!any) { lo = a; hi = b; any = true; }
         else { if (a < lo) lo = a; if (b > hi) hi = b; }
     };
-    // scan-line fill
     long long ex[4];
     int ne = 0;
     for (int i = 0; i < 4; i++) {
-        int j = (i + 3) & 3;  // pt0 = v[i-1], pt1 = v[i]
-        long long x0 = (long long)qx[j] << 16, x1 = (long long)qx[i] << 16;
-        int y0 = qy[j], y1 = qy[i];
+        const int j = (i + 3) & 3;  // pt0 = v[i-1], pt1 = v[i]
+        const long long x0 = qx[j], y0 = qy[j], x1 = qx[i], y1 = qy[i];
+        const bool outside = x0 < 0 || x0 >= w || x1 < 0 || x1 >= w || y0 < 0 || y0 >= h || y1 < 0 || y1 >= h;
+        long long cx0 = x0, cy0 = y0, cx1 = x1, cy1 = y1;
+        bool visible = true;
+        if (outside) visible = cv_clip_line(w, h, cx0, cy0, cx1, cy1);
+        // ---- boundary line between the clipped end points
+        if (visible) {
+            long long ax = cx0, ay = cy0, bx = cx1, by = cy1;
+            if (bx < ax) { long long t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
+            const long long adx = bx - ax, dy = by - ay, ady = dy < 0 ? -dy : dy;
+            const int sy = dy < 0 ? -1 : 1;
+            const long long t = (long long)(y - ay) * sy;
+            if (t >= 0 && t <= ady) {
+                if (adx >= ady) {  // x-major
+                    if (ady == 0) {
+                        add(ax, bx);
+                    } else {
+                        long long kmin = floor_div(adx * (2 * t - 1), 2 * ady) + 1;
+                        long long kmax = floor_div(adx * (2 * t + 1), 2 * ady);
+                        if (kmin < 0) kmin = 0;
+                        if (kmax > adx) kmax = adx;
+                        add(ax + kmin, ax + kmax);
+                    }
+                } else {  // y-major: one pixel per row
+                    const long long num = 2 * t * adx - ady, den = 2 * ady;
+                    long long m = -floor_div(-num, den);  // ceil
+                    if (m < 0) m = 0;
+                    add(ax + m, ax + m);
+                }
+            }
+        }
+        // ---- scan-line edge
         if (y0 == y1) continue;
-        long long dx = (x1 - x0) / (y1 - y0);
-        long long xs; int ya, yb;
-        if (y0 < y1) { ya = y0; yb = y1; xs = x0; } else { ya = y1; yb = y0; xs = x1; }
+        long long p0x = x0 << 16, p1x = x1 << 16, p0y = y0, p1y = y1;
+        if (outside) {
+            if (cy0 != cy1) { p0y = cy0; p1y = cy1; }
+            p0x = cx0 << 16;
+            p1x = cx1 << 16;
+        }
+        const long long dx = (p1x - p0x) / (p1y - p0y);   // C++ division: truncates toward zero, like OpenCV's
+        long long ya, yb, xs;
+        if (y0 < y1) { ya = y0; yb = y1; xs = p0x + (y0 - p0y) * dx; }
+        else { ya = y1; yb = y0; xs = p1x + (y1 - p1y) * dx; }
         if (y >= ya && y < yb) ex[ne++] = xs + (long long)(y - ya) * dx;
     }
     if (ne >= 2) {
         long long x1 = ex[0], x2 = ex[0];
         for (int i = 1; i < ne; i++) { if (ex[i] < x1) x1 = ex[i]; if (ex[i] > x2) x2 = ex[i]; }
-        add((x1 + 65535) >> 16, x2 >> 16);
-    }
-    // boundary lines (cv::LineIterator, 8-connected, drawn left to right, ties keep the minor coordinate)
-    for (int i = 0; i < 4; i++) {
-        int j = (i + 3) & 3;
-        int ax = qx[j], ay = qy[j], bx = qx[i], by = qy[i];
-        if (bx < ax) { int t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
-        long long adx = bx - ax, dy = by - ay, ady = dy < 0 ? -dy : dy;
-        int sy = dy < 0 ? -1 : 1;
-        long long t = (long long)(y - ay) * sy;
-        if (t < 0 || t > ady) continue;
-        if (adx >= ady) {  // x-major
-            if (ady == 0) { add(ax, bx); continue; }
-            long long kmin = floor_div(adx * (2 * t - 1), 2 * ady) + 1;
-            long long kmax = floor_div(adx * (2 * t + 1), 2 * ady);
-            if (kmin < 0) kmin = 0;
-            if (kmax > adx) kmax = adx;
-            add(ax + kmin, ax + kmax);
-        } else {  // y-major: one pixel per row
-            long long num = 2 * t * adx - ady, den = 2 * ady;
-            long long m = -floor_div(-num, den);  // ceil
-            if (m < 0) m = 0;
-            add(ax + m, ax + m);
-        }
+        const long long l = (x1 + 65535) >> 16, r = x2 >> 16;
+        if (l < w && r >= 0) add(l, r);
     }
     if (!any) return false;
     *xa = (int)lo;

@@ -250,10 +250,7 @@ __global__ void __launch_bounds__(kCandThreads) db_candidates(const float* __res
             int cnt = 0;
             for (int y = warp; y < wh; y += kCandThreads / 32) {
                 int xa, xb;
-                if (!dbpost::quad_row_span(qx, qy, y, &xa, &xb)) continue;
-                xa = max(xa, 0);
-                xb = min(xb, ww - 1);
-                if (xa > xb) continue;
+                if (!dbpost::quad_row_span(qx, qy, ww, wh, y, &xa, &xb)) continue;
                 const float* row = prob + fr.map_off + (win[1] + y) * fr.rw + win[0];
                 float part = 0.f;
                 for (int x = xa + lane; x <= xb; x += 32) part += row[x];
