@@ -182,6 +182,10 @@ def step_roofline(eng, E):
             op, kind = opk & 0xFF, opk >> 8
             if kind == 3:          # ran inside the previous step's fused kernel: fold its output bytes into that row
                 w_, n_, t_, b_, f_ = rows[-1]
+                if n_ == "conv_tc_kernel":
+                    # a 1x1 conv heading a fused squeeze-excite group: the step's time covers three launches (pool of the conv
+                    # input, gate, conv with the gate in its epilogue) — kept apart from the plain conv launches
+                    n_ = "se_conv_group(conv_tc+gpool+gate)"
                 prev_out = rows_out.pop()
                 rows[-1] = (w_, n_, t_ + float(t), b_ - prev_out + pout * eb_out + taps * cin * cout * 4, f_ + 2 * pout * cin * cout)
                 rows_out.append(pout * eb_out)
