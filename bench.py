@@ -268,6 +268,8 @@ def run_b200(args, rank, local_rank, world):
     dev = f"cuda:{local_rank}"
     if world > 1:
         import torch.distributed as dist
+        # NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr: stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     # one-time plan broadcast (rank 0 reads the packed plans; NCCL over NVLink)
     blobs = [weights.load_plan_blob(DET), weights.load_plan_blob(REC)] if rank == 0 else None
