@@ -175,26 +175,26 @@ class PlanInterpreter:
         return outs
 
     def _lstm(self, s: P.Step, x: torch.Tensor) -> torch.Tensor:
-        hidden, layers, ndir = s.p["hidden"], s.p["layers"], s.p["ndir"]
-        seq = x[:, :, 0, :].permute(2, 0, 1)  # [T,B,C]
-        for l in range(layers):
-            outs = []
-            for d in range(ndir):
-                k = l * ndir + d
-                w_ih, w_hh, b = self._w(s, f"w_ih{k}"), self._w(s, f"w_hh{k}"), self._w(s, f"b{k}")
-                inp = seq.flip(0) if d == 1 else seq
-                T, B, _ = inp.shape
-                h = torch.zeros(B, hidden)
-                c = torch.zeros(B, hidden)
-                xs = inp @ w_ih.t() + b
-                hs = []
-                for t in range(T):
-                    g = xs[t] + h @ w_hh.t()
-                    i, f, gg, o = g.chunk(4, dim=1)
-                    c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
-                    h = torch.sigmoid(o) * torch.tanh(c)
-                    hs.append(h)
-                hseq = torch.stack(hs, 0)
-                outs.append(hseq.flip(0) if d == 1 else hseq)
-            seq = torch.cat(outs, dim=2)
+        """Recurrent half of one (bi)LSTM layer.  ``x`` [B, ndir*4*hidden, 1, T] holds the gate pre-activations
+        W_ih x_t + b_ih + b_hh of every direction (the preceding CONV step); gate order i,f,g,o as in Paddle's ``rnn`` op
+        (oracle/graph_interp.py::_rnn follows the shipped V2/ch_rec graph, op#140).  The whole padded width is the sequence,
+        as in the reference (the recogniser pads each batch before the network)."""
+        hidden, ndir = s.p["hidden"], s.p["ndir"]
+        w_hh = self._w(s, "weight").reshape(ndir, 4 * hidden, hidden)
+        seq = x[:, :, 0, :].permute(2, 0, 1)  # [T,B,ndir*4H]
+        T, B, _ = seq.shape
+        outs = []
+        for d in range(ndir):
+            xs = seq[:, :, d * 4 * hidden:(d + 1) * 4 * hidden]
+            h = torch.zeros(B, hidden)
+            c = torch.zeros(B, hidden)
+            hs = [None] * T
+            for t in (range(T) if d == 0 else range(T - 1, -1, -1)):
+                g = xs[t] + h @ w_hh[d].t()
+                i, f, gg, o = g.chunk(4, dim=1)
+                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                hs[t] = h
+            outs.append(torch.stack(hs, 0))
+        seq = torch.cat(outs, dim=2)
         return seq.permute(1, 2, 0).unsqueeze(2).contiguous()

@@ -190,8 +190,15 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
                 o.sh = put_vec(pd.w(s, W_SHIFT), c, pad8(c));
                 break;
             }
-            case OP_LSTM:
-                throw InvalidArg{"LSTM step (V2/ch_rec) is not supported by this build"};
+            case OP_LSTM: {
+                const int hidden = s.p[P_HEADS], ndir = s.p[P_SCALE];
+                if (!lstm_supported(hidden) || ndir < 1 || ndir > 2) throw InvalidArg{"LSTM step: unsupported hidden size / directions"};
+                if (s.wsize[W_WEIGHT] != int64_t(ndir) * 4 * hidden * hidden || cin != ndir * 4 * hidden || cout != ndir * hidden)
+                    throw InvalidArg{"LSTM weight size mismatch"};
+                o.w = alloc(lstm_packed_weight_floats(hidden, ndir));
+                lstm_pack_weights(pd.w(s, W_WEIGHT), hidden, ndir, host.data() + o.w);
+                break;
+            }
             default:
                 break;
         }
@@ -866,6 +873,14 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 launch_softmax(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), static_cast<float*>(ptr_of(s.out)), vo.channels,
                                geo_of(s.out).total, prec, stream);
                 launches++;
+                break;
+            }
+            case OP_LSTM: {
+                if (value_cs(pd, s.ins[0]) < s.p[P_CIN] || value_cs(pd, s.out) < s.p[P_COUT]) throw InvalidArg{"LSTM value strides"};
+                VSE_CUDA(launch_lstm(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), ptr_of(s.out), value_cs(pd, s.out), d.w, tab_of(s.out),
+                                     cx.n_img, s.p[P_SCALE], prec, stream));
+                launches++;
+                cx.kind[k] = 2;
                 break;
             }
             default:

@@ -86,6 +86,15 @@ void launch_to_float(const void* in, int in_cs, int dtype_is_f32, float* out, in
 
 int attention_smem_bytes(int max_t, int dim);
 
+// lstm.cu — recurrent half of a (bi)LSTM layer: gates [pixels][ndir*4*hidden] (W_ih x + b, from the preceding CONV step)
+// -> out [pixels][ndir*hidden]; every image (H == 1) is one sequence over its padded width.  One 8-CTA cluster per
+// (direction, 4 lines) keeps W_hh resident in distributed shared memory.
+bool lstm_supported(int hidden);
+size_t lstm_packed_weight_floats(int hidden, int ndir);
+void lstm_pack_weights(const float* w_hh, int hidden, int ndir, float* dst);
+cudaError_t launch_lstm(const void* gates, int gates_cs, void* out, int out_cs, const float* w_packed, const ImgTab* tab, int n_img,
+                        int ndir, int prec, cudaStream_t st);
+
 // host table -> device through kernel parameters (no copy-engine traffic); returns the number of launches
 int launch_upload(void* dst, const void* src_host, size_t bytes, cudaStream_t st);
 

@@ -582,14 +582,24 @@ class _Lowerer:
         ndir = 2 if bidir else 1
         wl = [self.P[n] for n in op.inputs["WeightList"]]
         nw = layers * ndir
-        w = {}
-        for k in range(nw):
-            w[f"w_ih{k}"] = wl[2 * k].astype(np.float32)
-            w[f"w_hh{k}"] = wl[2 * k + 1].astype(np.float32)
-            w[f"b{k}"] = (wl[2 * nw + 2 * k] + wl[2 * nw + 2 * k + 1]).astype(np.float32)
-        vid = self.new_value(hidden * ndir)
-        self.emit(OP_LSTM, [x.vid], vid, i, p=dict(hidden=hidden, layers=layers, ndir=ndir,
-                                                  cin=self.values[x.vid].channels), w=w)
+        # One layer = the input GEMM of both directions as ONE 1x1 convolution (cin -> ndir*4*hidden gate pre-activations,
+        # b_ih + b_hh folded into its bias; runs on the tensor-core conv path) followed by the recurrent LSTM step, which
+        # only carries W_hh [ndir][4*hidden][hidden] (gate order i,f,g,o) and walks the time axis.
+        cur = x.vid
+        for l in range(layers):
+            cin = self.values[cur].channels
+            w_ih = np.concatenate([wl[2 * (l * ndir + d)] for d in range(ndir)], 0).astype(np.float32)        # [ndir*4H, cin]
+            w_hh = np.stack([wl[2 * (l * ndir + d) + 1] for d in range(ndir)], 0).astype(np.float32)          # [ndir, 4H, H]
+            b = np.concatenate([wl[2 * nw + 2 * (l * ndir + d)] + wl[2 * nw + 2 * (l * ndir + d) + 1] for d in range(ndir)], 0)
+            if w_ih.shape != (ndir * 4 * hidden, cin) or w_hh.shape != (ndir, 4 * hidden, hidden):
+                raise PlanError("rnn: unexpected weight shapes")
+            gates = self.new_value(ndir * 4 * hidden)
+            self.emit(OP_CONV, [cur], gates, i, p=dict(kh=1, kw=1, sh=1, sw=1, ph=0, pw=0, cin=cin, cout=ndir * 4 * hidden),
+                      w=dict(weight=w_ih.reshape(ndir * 4 * hidden, 1, 1, cin), bias=b.astype(np.float32)))
+            vid = self.new_value(hidden * ndir)
+            self.emit(OP_LSTM, [gates], vid, i, p=dict(hidden=hidden, ndir=ndir, cin=ndir * 4 * hidden, cout=hidden * ndir),
+                      w=dict(weight=w_hh))
+            cur = vid
         self.sym[op.out("Out")] = _Sym("img", vid, "tbc")
 
 
@@ -626,7 +636,7 @@ def _fuse(values: List[Value], nodes: List[Step], keep: set) -> List[Step]:
         if s.op in _EPI_OPS:
             cout = values[s.out].channels
             s1 = np.ones(cout, np.float64)
-            b1 = np.zeros(cout, np.float64)
+            b1 = s.w["bias"].astype(np.float64) if "bias" in s.w else np.zeros(cout, np.float64)   # e.g. the LSTM input GEMM
             s2 = np.ones(cout, np.float64)
             b2 = np.zeros(cout, np.float64)
             act1, act2, res = ACT_NONE, ACT_NONE, -1
@@ -754,7 +764,7 @@ _P_SLOTS = ["kh", "kw", "sh", "sw", "ph", "pw", "cin", "cout", "act", "act2", "h
 _F_SLOTS = ["hs_slope", "hs_offset", "eps", "qscale"]
 _W_SLOTS = ["weight", "bias", "post_scale", "post_shift", "gamma", "beta", "scale", "shift"]
 _COPY_P = {"coff": "scale", "c": "cout"}           # COPY reuses slots
-_LSTM_P = {"hidden": "heads", "layers": "dim", "ndir": "scale"}
+_LSTM_P = {"hidden": "heads", "ndir": "scale"}
 
 
 @dataclass
@@ -832,17 +842,9 @@ class Plan:
                     pass
                 else:
                     raise PlanError(f"unknown step param {k}")
-            if s.op == OP_LSTM:
-                order = []
-                nw = s.p["layers"] * s.p["ndir"]
-                for k in range(nw):
-                    order += [s.w[f"w_ih{k}"].reshape(-1), s.w[f"w_hh{k}"].reshape(-1), s.w[f"b{k}"].reshape(-1)]
-                arr = np.concatenate(order)
-                wslots[0], wsizes[0] = add_w(arr), arr.size
-            else:
-                for k, arr in s.w.items():
-                    j = _W_SLOTS.index(k)
-                    wslots[j], wsizes[j] = add_w(arr), int(np.asarray(arr).size)
+            for k, arr in s.w.items():
+                j = _W_SLOTS.index(k)
+                wslots[j], wsizes[j] = add_w(arr), int(np.asarray(arr).size)
             srec += struct.pack(f"<i{_N_INS}ii{_N_P}i{_N_F}f{_N_W}q{_N_W}q", s.op, *ins, s.out, *p, *f, *wslots, *wsizes)
         weights = np.concatenate(wchunks) if wchunks else np.zeros(0, np.float32)
         name_b = self.name.encode()[:63].ljust(64, b"\0")
@@ -941,7 +943,7 @@ def deserialize(blob: bytes) -> Plan:
         if op == OP_COPY:
             p["coff"], p["c"] = p["scale"], p["cout"]
         if op == OP_LSTM:
-            p["hidden"], p["layers"], p["ndir"] = p["heads"], p["dim"], p["scale"]
+            p["hidden"], p["ndir"] = p["heads"], p["scale"]
         w: Dict[str, np.ndarray] = {}
         for j, k in enumerate(_W_SLOTS):
             if wo[j] >= 0:
@@ -956,16 +958,7 @@ def deserialize(blob: bytes) -> Plan:
         elif op == OP_VECLIN:
             w["weight"] = w["weight"].reshape(cout, cin)
         elif op == OP_LSTM:
-            flat = w.pop("weight")
-            hidden, layers, ndir, c_in = p["hidden"], p["layers"], p["ndir"], cin
-            o = 0
-            for l in range(layers):
-                isz = c_in if l == 0 else hidden * ndir
-                for d in range(ndir):
-                    k = l * ndir + d
-                    w[f"w_ih{k}"] = flat[o:o + 4 * hidden * isz].reshape(4 * hidden, isz); o += 4 * hidden * isz
-                    w[f"w_hh{k}"] = flat[o:o + 4 * hidden * hidden].reshape(4 * hidden, hidden); o += 4 * hidden * hidden
-                    w[f"b{k}"] = flat[o:o + 4 * hidden]; o += 4 * hidden
+            w["weight"] = w["weight"].reshape(p["ndir"], 4 * p["hidden"], p["hidden"])
         steps.append(Step(op, ins, out, p, w))
     return Plan(values=values, steps=steps, input_vid=input_vid, output_vids=outs, name=name,
                 norm_scale=tuple(norm[:3]), norm_shift=tuple(norm[3:]), h1_values=tuple(h1))

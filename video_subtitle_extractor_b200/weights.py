@@ -16,7 +16,7 @@ from .loader import load_model
 
 WEIGHTS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights")
 DEFAULT_MODELS = ["V4/ch_det_fast", "V4/en_rec_fast"]
-EXTRA_MODELS = ["V4/ch_rec_fast", "V3/japan_rec_fast", "V3/korean_rec_fast", "V4/ch_det", "V4/ch_rec"]
+EXTRA_MODELS = ["V4/ch_rec_fast", "V3/japan_rec_fast", "V3/korean_rec_fast", "V4/ch_det", "V4/ch_rec", "V2/ch_rec"]
 
 
 def _path(name: str) -> str:
