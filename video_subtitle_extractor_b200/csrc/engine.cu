@@ -683,10 +683,15 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 };
                 if (s.op == OP_DWCONV) {
                     if (out_f32) throw InvalidArg{"depthwise conv cannot produce a fetched output"};
-                    static const int dw_mode = [] { const char* e = getenv("VSE_DW_MODE"); return e ? atoi(e) : 1; }();   // 0 strip, 1 tiled
+                    // 0 strip, 1 shared-memory tiled, 2 (default) register tiled, 3 per layer: register tiled from
+                    // VSE_DW_REG_MIN_C channels up, shared-memory tiled below
+                    static const int dw_mode = [] { const char* e = getenv("VSE_DW_MODE"); return e ? atoi(e) : 2; }();
+                    static const int dw_reg_min_c = [] { const char* e = getenv("VSE_DW_REG_MIN_C"); return e ? atoi(e) : 64; }();
                     int mh = 0, mw = 0;
                     for (const ImgTab& t : geo_of(s.out).tab) { mh = std::max(mh, t.h); mw = std::max(mw, t.w); }
-                    if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && dw_mode == 1 && launch_dwconv_tiled(a, mh, mw, stream)) cx.kind[k] = 2;
+                    const bool use_reg = dw_mode == 2 || (dw_mode == 3 && a.cin_pad >= dw_reg_min_c);
+                    if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && use_reg && launch_dwconv_reg(a, mh, mw, stream)) cx.kind[k] = 2;
+                    else if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && dw_mode >= 1 && launch_dwconv_tiled(a, mh, mw, stream)) cx.kind[k] = 2;
                     else if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
                     else launch_dwconv(a, prec, stream);
                 } else if (s.op == OP_DECONV2) {

@@ -12,6 +12,7 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "plan.h"
@@ -313,6 +314,190 @@ bool launch_dwconv_tiled(const ConvArgs& a, int max_out_h, int max_out_w, cudaSt
         default: return false;
     }
 #undef VSE_DW_TILE
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise KxK, register tiled: one thread = TH x TW output pixels of ONE channel pair (half2).  The whole filter of the
+// pair (K*K float2) and the output tile live in registers; the input patch is read row by row straight from global
+// memory (4-byte loads: a warp reads 128 contiguous bytes = 64 channels of one pixel), converted once, and every
+// converted value feeds up to K*K FMAs — no shared memory, no per-strip filter reloads.  The kernels above issue one
+// 16-byte shared/global load per ~10 FMAs plus the fp16->fp32 conversions of 8 channels per strip column and are
+// instruction-issue bound on the deep (>= 96 channel, 5x5) layers; here ~80 % of the issued instructions are FMAs.
+// Accumulation order per output (ky, then kx ascending, fp32 fmaf from 0) is the same as in the other depthwise kernels,
+// so the results are bit-identical to theirs.
+// ------------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE fp32 operations per issued instruction, each lane
+// rounded exactly like the scalar instruction) and a one-instruction 64-bit address  base + a * b  (IMAD.WIDE.U32)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ const char* addr_mad(const char* base, unsigned a, unsigned b) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(reinterpret_cast<unsigned long long>(base)));
+    return reinterpret_cast<const char*>(d);
+}
+template <int ACT>
+__device__ __forceinline__ float2 fact2(float2 v) {
+    if constexpr (ACT == ACT_RELU) return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+    else if constexpr (ACT == ACT_HSWISH) {   // x * min(max(x + 3, 0), 6) * (1/6), evaluated left to right as fact<>()
+        const float2 t = fadd2(v, make_float2(3.f, 3.f));
+        const float2 c = make_float2(fminf(fmaxf(t.x, 0.f), 6.f), fminf(fmaxf(t.y, 0.f), 6.f));
+        return fmul2(fmul2(v, c), make_float2(1.f / 6.f, 1.f / 6.f));
+    } else return v;
+}
+
+template <int K, int SH, int SW, int TH, int TW, int ACT>
+__global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x, int tiles_y) {
+    constexpr int IH = (TH - 1) * SH + K, IW = (TW - 1) * SW + K;
+    const int img = blockIdx.y;
+    const ImgTab ti = p.tin[img], to = p.tout[img];
+    const int cp2 = p.cvecs * 4;                          // channel pairs per pixel
+    const unsigned idx = blockIdx.x * 128u + threadIdx.x;   // the launcher keeps tiles * pairs below 2^31
+    const unsigned tile = idx / unsigned(cp2);
+    const int pair = int(idx - tile * unsigned(cp2));
+    if (tile >= unsigned(tiles_x * tiles_y)) return;
+    const int ty = int(tile / unsigned(tiles_x)), tx = int(tile) - ty * tiles_x;
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    if (oy0 >= to.h || ox0 >= to.w) return;
+    const int c0 = pair * 2;
+    const int iy0 = oy0 * SH - p.ph, ix0 = ox0 * SW - p.pw;
+    const char* base = reinterpret_cast<const char*>(p.in + size_t(ti.off) * p.in_cs + c0);
+    const unsigned cstep = unsigned(p.in_cs) * 2u;        // bytes per pixel
+    // The whole input patch goes into registers first (packed half2, one register per tap): all IH*IW loads of a thread
+    // are in flight together, so a thread pays ONE memory round trip instead of one per patch row — on these small,
+    // L2-resident maps the dependent round trips were half the run time of the row-by-row variants.  Every address is one
+    // IMAD.WIDE.  Out-of-image taps are predicated loads that yield 0 (the FMAs then add +0).
+    unsigned xin[IH][IW];
+    const bool interior = iy0 >= 0 && iy0 + IH <= ti.h && ix0 >= 0 && ix0 + IW <= ti.w;
+    if (interior) {
+        const char* pp = addr_mad(base, unsigned(iy0 * ti.w + ix0), cstep);
+        const unsigned rstep = unsigned(ti.w) * cstep;    // bytes per image row (< 2^32: checked by the launcher)
+#pragma unroll
+        for (int r = 0; r < IH; r++) {
+            const char* rowp = addr_mad(pp, unsigned(r), rstep);
+#pragma unroll
+            for (int i = 0; i < IW; i++) xin[r][i] = __ldg(reinterpret_cast<const unsigned*>(addr_mad(rowp, unsigned(i), cstep)));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < IH; r++) {
+            const int iy = iy0 + r;
+            const bool row_ok = iy >= 0 && iy < ti.h;
+            const int roff = (row_ok ? iy : 0) * ti.w;   // in-image pixel offsets fit 32 bits (engine: pixel index < 2^31)
+#pragma unroll
+            for (int i = 0; i < IW; i++) {
+                const int ix = ix0 + i;
+                unsigned v = 0u;
+                if (row_ok && ix >= 0 && ix < ti.w) v = __ldg(reinterpret_cast<const unsigned*>(addr_mad(base, unsigned(roff + ix), cstep)));
+                xin[r][i] = v;
+            }
+        }
+    }
+    float2 w[K * K];
+    {
+        const char* wp = reinterpret_cast<const char*>(p.w + c0);
+        const unsigned wstep = unsigned(p.cp) * 4u;
+#pragma unroll
+        for (int t = 0; t < K * K; t++) w[t] = __ldg(reinterpret_cast<const float2*>(addr_mad(wp, unsigned(t), wstep)));
+    }
+    float2 acc[TH][TW];
+#pragma unroll
+    for (int a = 0; a < TH; a++)
+#pragma unroll
+        for (int b = 0; b < TW; b++) acc[a][b] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < IH; r++) {
+        float2 x[IW];
+#pragma unroll
+        for (int i = 0; i < IW; i++) x[i] = __half22float2(*reinterpret_cast<const __half2*>(&xin[r][i]));
+#pragma unroll
+        for (int a = 0; a < TH; a++) {
+            const int ky = r - a * SH;   // compile-time after unrolling
+            if (ky < 0 || ky >= K) continue;
+#pragma unroll
+            for (int i = 0; i < IW; i++) {
+#pragma unroll
+                for (int b = 0; b < TW; b++) {
+                    const int kx = i - b * SW;
+                    if (kx >= 0 && kx < K) acc[a][b] = ffma2(x[i], w[ky * K + kx], acc[a][b]);
+                }
+            }
+        }
+    }
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
+    const bool post = p.ps != nullptr;
+    float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+    if (post) {
+        sc = __ldg(reinterpret_cast<const float2*>(p.ps + c0));
+        sh = __ldg(reinterpret_cast<const float2*>(p.pt + c0));
+    }
+    char* obase = reinterpret_cast<char*>(p.out + (size_t(to.off) + size_t(oy0) * to.w + ox0) * p.out_cs + c0);
+    const unsigned ocstep = unsigned(p.out_cs) * 2u, orstep = unsigned(to.w) * ocstep;
+    const bool full = oy0 + TH <= to.h && ox0 + TW <= to.w;
+#pragma unroll
+    for (int a = 0; a < TH; a++) {
+        if (!full && oy0 + a >= to.h) break;
+        char* orow = const_cast<char*>(addr_mad(obase, unsigned(a), orstep));
+#pragma unroll
+        for (int b = 0; b < TW; b++) {
+            if (!full && ox0 + b >= to.w) break;
+            float2 v = fact2<ACT>(fadd2(acc[a][b], bias));
+            if (post) v = ffma2(v, sc, sh);
+            *reinterpret_cast<__half2*>(const_cast<char*>(addr_mad(orow, unsigned(b), ocstep))) = __floats2half2_rn(v.x, v.y);
+        }
+    }
+}
+
+template <int K, int SH, int SW, int TH, int TW>
+static bool dw_reg_launch(const DwDev& d, const ConvArgs& a, int max_h, int max_w, cudaStream_t st) {
+    const int tiles_x = (max_w + TW - 1) / TW, tiles_y = (max_h + TH - 1) / TH;
+    if (int64_t(tiles_x) * tiles_y * d.cvecs * 4 > 0x7fffff00LL) return false;
+    if (int64_t(max_w) * std::max(SW, 1) * std::max(a.in_cs, a.out_cs) * 2 * 2 > 0x7fffffffLL) return false;   // 32-bit row strides
+    dim3 grid(cdiv_i(int64_t(tiles_x) * tiles_y * d.cvecs * 4, 128), a.n_img);
+    switch (a.epi.act) {
+        case ACT_NONE: dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_NONE><<<grid, 128, 0, st>>>(d, tiles_x, tiles_y); return true;
+        case ACT_RELU: dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_RELU><<<grid, 128, 0, st>>>(d, tiles_x, tiles_y); return true;
+        case ACT_HSWISH: dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_HSWISH><<<grid, 128, 0, st>>>(d, tiles_x, tiles_y); return true;
+        default: return false;
+    }
+}
+
+bool launch_dwconv_reg(const ConvArgs& a, int max_out_h, int max_out_w, cudaStream_t st) {
+    if (a.epi.res || a.epi.act2 != ACT_NONE || a.out_f32 || a.kh != a.kw) return false;
+    if (2 * a.ph != a.kh - 1 || 2 * a.pw != a.kw - 1) return false;
+    DwDev d{static_cast<const __half*>(a.in), static_cast<__half*>(a.out), a.w, a.epi.bias, a.epi.post_scale, a.epi.post_shift,
+            a.tin, a.tout, a.in_cs, a.out_cs, a.cin_pad / 8, a.cin_pad, a.ph, a.pw};
+    if (!d.bias) return false;
+    // rows per tile: 3 or 4, whichever pads the tallest image less (ties: 4)
+    const bool th3 = ((max_out_h + 2) / 3) * 3 < ((max_out_h + 3) / 4) * 4;
+    const int key = a.kh * 100 + a.sh * 10 + a.sw;
+#define VSE_DW_REG(KK, SHH, SWW) \
+    (th3 ? dw_reg_launch<KK, SHH, SWW, 3, 4>(d, a, max_out_h, max_out_w, st) : dw_reg_launch<KK, SHH, SWW, 4, 4>(d, a, max_out_h, max_out_w, st))
+    switch (key) {
+        case 311: return VSE_DW_REG(3, 1, 1);
+        case 322: return VSE_DW_REG(3, 2, 2);
+        case 321: return VSE_DW_REG(3, 2, 1);
+        case 312: return VSE_DW_REG(3, 1, 2);
+        case 511: return VSE_DW_REG(5, 1, 1);
+        case 522: return VSE_DW_REG(5, 2, 2);
+        case 521: return VSE_DW_REG(5, 2, 1);
+        case 512: return VSE_DW_REG(5, 1, 2);
+        default: return false;
+    }
+#undef VSE_DW_REG
 }
 
 // ------------------------------------------------------------------------------------------------

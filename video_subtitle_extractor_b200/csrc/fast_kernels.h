@@ -15,6 +15,9 @@ bool launch_dwconv_fast(const ConvArgs& a, int max_strip_units, cudaStream_t st)
 // same layers, shared-memory tiled with cp.async staging (max_out_h / max_out_w: largest output image of the batch)
 bool launch_dwconv_tiled(const ConvArgs& a, int max_out_h, int max_out_w, cudaStream_t st);
 
+// same layers, register tiled: one thread = 3|4 x 4 outputs of one channel pair, filter and tile in registers, no shared memory
+bool launch_dwconv_reg(const ConvArgs& a, int max_out_h, int max_out_w, cudaStream_t st);
+
 // 3x3 stride-2 stem on uint8 BGRX input, 16 output channels.  max_out_pix_pairs = max over images of out_h * ceil(out_w / 2).
 bool launch_stem_fast(const ConvArgs& a, int cout, int max_out_pix_pairs, cudaStream_t st);
 
