@@ -9,6 +9,7 @@
 //     into its 4x4 patch of the probability map; the 272x480x24 intermediate never goes to HBM.
 // The engine falls back to the generic kernels for any other shape.
 #include "fast_kernels.h"
+#include "pdl.cuh"
 
 #include <cuda_fp16.h>
 
@@ -57,6 +58,8 @@ struct DwDev {
 
 template <int K, int SH, int SW, int TW, int ACT>
 __global__ void __launch_bounds__(256) dwconv_fast_kernel(DwDev p) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int img = blockIdx.y;
     const ImgTab ti = p.tin[img], to = p.tout[img];
     const int strips = (to.w + TW - 1) / TW;
@@ -137,9 +140,9 @@ static bool dw_launch_act(const DwDev& d, const ConvArgs& a, int max_out_w_strip
     // h * strips <= (pix + h * (TW - 1)) / TW <= pix (for TW >= 1) — use pix / TW + h_max as a safe bound via max_out_pix
     dim3 grid(cdiv_i(int64_t(max_out_w_strips_pix) * d.cvecs, 256), a.n_img);
     switch (a.epi.act) {
-        case ACT_NONE: dwconv_fast_kernel<K, SH, SW, TW, ACT_NONE><<<grid, 256, 0, st>>>(d); return true;
-        case ACT_RELU: dwconv_fast_kernel<K, SH, SW, TW, ACT_RELU><<<grid, 256, 0, st>>>(d); return true;
-        case ACT_HSWISH: dwconv_fast_kernel<K, SH, SW, TW, ACT_HSWISH><<<grid, 256, 0, st>>>(d); return true;
+        case ACT_NONE: pdl_launch(dwconv_fast_kernel<K, SH, SW, TW, ACT_NONE>, grid, 256, 0, st, d); return true;
+        case ACT_RELU: pdl_launch(dwconv_fast_kernel<K, SH, SW, TW, ACT_RELU>, grid, 256, 0, st, d); return true;
+        case ACT_HSWISH: pdl_launch(dwconv_fast_kernel<K, SH, SW, TW, ACT_HSWISH>, grid, 256, 0, st, d); return true;
         default: return false;
     }
 }
@@ -178,6 +181,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int K, int SH, int SW, int TH, int CBV, int ACT>
 __global__ void __launch_bounds__(TH * 4 * CBV) dwconv_tile_kernel(DwDev p, int tiles_x) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     constexpr int TW = 16, ST = 4;                       // 16 output columns per tile, strips of 4
     constexpr int IH = (TH - 1) * SH + K, IWT = (TW - 1) * SW + K;
     constexpr int NT = TH * 4 * CBV;
@@ -279,7 +284,7 @@ static bool dw_tile_launch(const DwDev& d, const ConvArgs& a, int max_h, int max
     auto go = [&](auto kern) {
         // > 48 KB of dynamic shared memory needs the opt-in (per device and per kernel instantiation; the call is cheap)
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        kern<<<grid, TH * 4 * CBV, smem, st>>>(d, tiles_x);
+        pdl_launch(kern, grid, TH * 4 * CBV, smem, st, d, tiles_x);
     };
     switch (a.epi.act) {
         case ACT_NONE: go(dwconv_tile_kernel<K, SH, SW, TH, CBV, ACT_NONE>); return true;
@@ -361,6 +366,8 @@ __device__ __forceinline__ float2 fact2(float2 v) {
 
 template <int K, int SH, int SW, int TH, int TW, int ACT>
 __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x, int tiles_y) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     constexpr int IH = (TH - 1) * SH + K, IW = (TW - 1) * SW + K;
     const int img = blockIdx.y;
     const ImgTab ti = p.tin[img], to = p.tout[img];
@@ -468,9 +475,9 @@ static bool dw_reg_launch(const DwDev& d, const ConvArgs& a, int max_h, int max_
     if (int64_t(max_w) * std::max(SW, 1) * std::max(a.in_cs, a.out_cs) * 2 * 2 > 0x7fffffffLL) return false;   // 32-bit row strides
     dim3 grid(cdiv_i(int64_t(tiles_x) * tiles_y * d.cvecs * 4, 128), a.n_img);
     switch (a.epi.act) {
-        case ACT_NONE: dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_NONE><<<grid, 128, 0, st>>>(d, tiles_x, tiles_y); return true;
-        case ACT_RELU: dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_RELU><<<grid, 128, 0, st>>>(d, tiles_x, tiles_y); return true;
-        case ACT_HSWISH: dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_HSWISH><<<grid, 128, 0, st>>>(d, tiles_x, tiles_y); return true;
+        case ACT_NONE: pdl_launch(dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_NONE>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
+        case ACT_RELU: pdl_launch(dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_RELU>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
+        case ACT_HSWISH: pdl_launch(dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_HSWISH>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
         default: return false;
     }
 }
@@ -511,6 +518,8 @@ struct StemDev {
 
 template <int ACT>
 __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     __shared__ __align__(16) float sw[27 * 16];   // [(ky*3+kx)*3 + ci][co]
     __shared__ float sb[16];
     for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) {
@@ -589,9 +598,9 @@ bool launch_stem_fast(const ConvArgs& a, int cout, int max_out_pix_pairs, cudaSt
               a.out_cs, a.w_ci, a.w_co, a.epi.act, {a.nscale[0], a.nscale[1], a.nscale[2]}, {a.nshift[0], a.nshift[1], a.nshift[2]}};
     dim3 grid(cdiv_i(max_out_pix_pairs, 128), a.n_img);
     switch (a.epi.act) {
-        case ACT_NONE: stem_fast_kernel<ACT_NONE><<<grid, 128, 0, st>>>(d); return true;
-        case ACT_RELU: stem_fast_kernel<ACT_RELU><<<grid, 128, 0, st>>>(d); return true;
-        case ACT_HSWISH: stem_fast_kernel<ACT_HSWISH><<<grid, 128, 0, st>>>(d); return true;
+        case ACT_NONE: pdl_launch(stem_fast_kernel<ACT_NONE>, grid, 128, 0, st, d); return true;
+        case ACT_RELU: pdl_launch(stem_fast_kernel<ACT_RELU>, grid, 128, 0, st, d); return true;
+        case ACT_HSWISH: pdl_launch(stem_fast_kernel<ACT_HSWISH>, grid, 128, 0, st, d); return true;
         default: return false;
     }
 }
@@ -608,6 +617,8 @@ struct HeadDev {
 
 template <int C>
 __global__ void __launch_bounds__(128, 4) db_head_fused_kernel(HeadDev p) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     __shared__ __align__(16) float sw1[4 * C * C];
     __shared__ __align__(16) float sw2[4 * C];
     __shared__ float sb1[C];
@@ -667,7 +678,7 @@ bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, con
     if (reinterpret_cast<uintptr_t>(out) & 15) return false;
     HeadDev d{static_cast<const __half*>(in), out, w1, b1, w2, b2, tin, tout, in_cs};
     dim3 grid(cdiv_i(max_in_pix, 128), n_img);
-    db_head_fused_kernel<24><<<grid, 128, 0, st>>>(d);
+    pdl_launch(db_head_fused_kernel<24>, grid, 128, 0, st, d);
     return true;
 }
 
@@ -726,6 +737,8 @@ __device__ __forceinline__ void cta_fc(const float* in, int n_in, const float* _
 }
 
 __global__ void __launch_bounds__(512) se_gate_kernel(SeDev p) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     extern __shared__ float sm[];
     float* mean = sm;                 // [c]
     float* hid = sm + p.c;            // [cm]
@@ -760,7 +773,7 @@ void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, 
     SeDev d{partial, splits, c_pad, c, cm, tin, w1, b1, w2, b2, act1, act2, slope1, offset1, slope2, offset2, out,
             pre_w, pre_b, cx, cx_pad, pre_ld};
     const int threads = 512;   // cm <= threads is checked by the caller
-    se_gate_kernel<<<n_img, threads, size_t(c + cm + threads + (pre_w ? cx : 0)) * sizeof(float), st>>>(d);
+    pdl_launch(se_gate_kernel, n_img, threads, size_t(c + cm + threads + (pre_w ? cx : 0)) * sizeof(float), st, d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -775,6 +788,8 @@ struct GatherDev {
 };
 
 __global__ void __launch_bounds__(256) concat_gather_kernel(GatherDev p) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     // grid: x over (column, 16-byte piece) of one output row, y = row, z = image: one integer division per thread
     const int img = blockIdx.z, oy = blockIdx.y;
     const ImgTab to = p.tout[img];
@@ -815,7 +830,7 @@ void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n
         d.s[i].shift = sh;
     }
     dim3 grid(cdiv_i(int64_t(max_out_w) * d.total_cvecs, 256), max_out_h, n_img);
-    concat_gather_kernel<<<grid, 256, 0, st>>>(d);
+    pdl_launch(concat_gather_kernel, grid, 256, 0, st, d);
 }
 
 }  // namespace vse

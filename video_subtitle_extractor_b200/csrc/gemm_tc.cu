@@ -13,6 +13,7 @@
 // warps 2-5 = epilogue.  These nets are HBM-bound (35-59 FLOP/B): the point of the tensor cores is to get the FMA work
 // out of the way so that the kernel streams activations at memory speed.
 #include "gemm_tc.h"
+#include "pdl.cuh"
 
 #include <cuda_fp16.h>
 
@@ -588,17 +589,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int taps = p.kh * p.kw;
     const int k_iters = (p.halo ? 1 : p.rowbox ? p.kw : taps) * p.num_kb;
 
+    // Everything up to here (and the resident weight load below) touches only kernel parameters and static weights, so
+    // under programmatic dependent launch (pdl.cuh) it overlaps the tail of the previous step's kernel; activations,
+    // residuals and gates are first touched after pdl_wait().
+    if (warp == 0 && lane == 0 && p.b_resident) {
+        mbar_expect_tx(b_full, uint32_t(p.b_total));
+        for (int tp = 0; tp < taps; tp++)
+            for (int kb = 0; kb < p.num_kb; kb++)
+                tma_load_2d(bres + size_t(tp * p.num_kb + kb) * p.n_chunk * 128, &map_b, b_full, tp * p.k_pad + kb * p.kb_elems, 0);
+    }
+    pdl_wait();
+    pdl_trigger();
+
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             int stage = 0;
             uint32_t phase = 0;
-            if (p.b_resident) {
-                mbar_expect_tx(b_full, uint32_t(p.b_total));
-                for (int tp = 0; tp < taps; tp++)
-                    for (int kb = 0; kb < p.num_kb; kb++)
-                        tma_load_2d(bres + size_t(tp * p.num_kb + kb) * p.n_chunk * 128, &map_b, b_full, tp * p.k_pad + kb * p.kb_elems, 0);
-            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
                 int img = 0, y0 = 0, x0 = 0;
@@ -888,7 +895,7 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     }
     const int total = t.num_m_tiles * t.n_chunks;
     const int grid = std::max(1, std::min(total, sm_count));
-    conv_tc_kernel<<<grid, kThreads, smem, st>>>(t.map_a, t.map_b, t.map_o, p);
+    pdl_launch(conv_tc_kernel, grid, kThreads, smem, st, t.map_a, t.map_b, t.map_o, p);
     return "";
 }
 

@@ -8,6 +8,7 @@
 //   conv2d / depthwise_conv2d / conv2d_transpose(2x2,s2) / pool2d / nearest_interp_v2 / layer_norm /
 //   softmax / SVTR attention (backend/models/V4/en_rec_fast/inference.pdmodel ops #227-284).
 #include "nn_kernels.h"
+#include "pdl.cuh"
 
 #include <cuda_fp16.h>
 #include <cfloat>
@@ -135,6 +136,8 @@ __device__ __forceinline__ void conv_load_a<unsigned char>(const ConvDev& p, con
 
 template <typename InT, typename OutT, int TN>
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvDev p) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     constexpr int BM = 64, BK = 16, BN = 16 * TN, LDA = BM + 4;
     __shared__ __align__(16) float As[BK][LDA];
     __shared__ __align__(16) float Bs[BK][BN];
@@ -230,10 +233,10 @@ static void conv_simt_dispatch(const ConvArgs& a, cudaStream_t st) {
     int tiles_m = cdiv(a.max_out_pix, 64);
     if (a.cout_store <= 32) {
         dim3 grid(tiles_m, cdiv(a.cout_store, 32), a.n_img);
-        conv_simt_kernel<InT, OutT, 2><<<grid, 256, 0, st>>>(d);
+        pdl_launch(conv_simt_kernel<InT, OutT, 2>, grid, 256, 0, st, d);
     } else {
         dim3 grid(tiles_m, cdiv(a.cout_store, 64), a.n_img);
-        conv_simt_kernel<InT, OutT, 4><<<grid, 256, 0, st>>>(d);
+        pdl_launch(conv_simt_kernel<InT, OutT, 4>, grid, 256, 0, st, d);
     }
 }
 
@@ -252,6 +255,8 @@ void launch_conv_simt(const ConvArgs& a, int prec, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(ConvDev p, int cvecs) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int img = blockIdx.y;
     const ImgTab ti = p.tin[img], to = p.tout[img];
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -292,8 +297,8 @@ void launch_dwconv(const ConvArgs& a, int prec, cudaStream_t st) {
     ConvDev d = to_dev(a);
     int cvecs = a.cin_pad / 8;
     dim3 grid(cdiv(int64_t(a.max_out_pix) * cvecs, 256), a.n_img);
-    if (prec == 0) dwconv_kernel<__half><<<grid, 256, 0, st>>>(d, cvecs);
-    else dwconv_kernel<float><<<grid, 256, 0, st>>>(d, cvecs);
+    if (prec == 0) pdl_launch(dwconv_kernel<__half>, grid, 256, 0, st, d, cvecs);
+    else pdl_launch(dwconv_kernel<float>, grid, 256, 0, st, d, cvecs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -302,6 +307,8 @@ void launch_dwconv(const ConvArgs& a, int prec, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) deconv2_kernel(ConvDev p, int cout, int cgroups, int cout_pad) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int img = blockIdx.y;
     const ImgTab ti = p.tin[img], to = p.tout[img];
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -347,8 +354,8 @@ void launch_deconv2(const ConvArgs& a, int cout, int prec, cudaStream_t st) {
     ConvDev d = to_dev(a);
     int cgroups = cdiv(cout, 8);
     dim3 grid(cdiv(int64_t(a.max_out_pix) * cgroups, 256), a.n_img);
-    if (prec == 0) deconv2_kernel<__half><<<grid, 256, 0, st>>>(d, cout, cgroups, cgroups * 8);
-    else deconv2_kernel<float><<<grid, 256, 0, st>>>(d, cout, cgroups, cgroups * 8);
+    if (prec == 0) pdl_launch(deconv2_kernel<__half>, grid, 256, 0, st, d, cout, cgroups, cgroups * 8);
+    else pdl_launch(deconv2_kernel<float>, grid, 256, 0, st, d, cout, cgroups, cgroups * 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -357,6 +364,8 @@ void launch_deconv2(const ConvArgs& a, int cout, int prec, cudaStream_t st) {
 template <typename T>
 __global__ void __launch_bounds__(256) gpool_partial_kernel(const T* in, int in_cs, int cvecs, const ImgTab* tin,
                                                            float* partial, int splits) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     __shared__ float red[256][8];
     const int img = blockIdx.y, split = blockIdx.x;
     const ImgTab ti = tin[img];
@@ -413,6 +422,8 @@ __global__ void __launch_bounds__(256) gpool_partial_kernel(const T* in, int in_
 }
 
 __global__ void gpool_final_kernel(const float* partial, int splits, int c_pad, const ImgTab* tin, float* out, int out_c) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int img = blockIdx.x;
     const float inv = 1.f / float(tin[img].h * tin[img].w);
     for (int c = threadIdx.x; c < out_c; c += blockDim.x) {
@@ -425,14 +436,14 @@ __global__ void gpool_final_kernel(const float* partial, int splits, int c_pad, 
 void launch_gpool_partial(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n_img, float* partial, int splits,
                           int prec, cudaStream_t st) {
     dim3 grid(splits, n_img);
-    if (prec == 0) gpool_partial_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), in_cs, c_pad / 8, tin, partial, splits);
-    else gpool_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), in_cs, c_pad / 8, tin, partial, splits);
+    if (prec == 0) pdl_launch(gpool_partial_kernel<__half>, grid, 256, 0, st, static_cast<const __half*>(in), in_cs, c_pad / 8, tin, partial, splits);
+    else pdl_launch(gpool_partial_kernel<float>, grid, 256, 0, st, static_cast<const float*>(in), in_cs, c_pad / 8, tin, partial, splits);
 }
 
 void launch_gpool(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n_img, int max_pix, float* partial,
                   int splits, float* out, int out_c, int prec, cudaStream_t st) {
     launch_gpool_partial(in, in_cs, c_pad, tin, n_img, partial, splits, prec, st);
-    gpool_final_kernel<<<n_img, 128, 0, st>>>(partial, splits, c_pad, tin, out, out_c);
+    pdl_launch(gpool_final_kernel, n_img, 128, 0, st, partial, splits, c_pad, tin, out, out_c);
     (void)max_pix;
 }
 
@@ -440,6 +451,8 @@ void launch_gpool(const void* in, int in_cs, int c_pad, const ImgTab* tin, int n
 // VECLIN: tiny fully-connected layer on pooled vectors (SE blocks)
 // ------------------------------------------------------------------------------------------------
 __global__ void veclin_kernel(const float* in, int cin, float* out, int cout, const float* w, EpiDev e) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     extern __shared__ float xin[];
     const int img = blockIdx.x;
     for (int i = threadIdx.x; i < cin; i += blockDim.x) xin[i] = in[size_t(img) * cin + i];
@@ -457,7 +470,7 @@ __global__ void veclin_kernel(const float* in, int cin, float* out, int cout, co
 
 void launch_veclin(const float* in, int cin, float* out, int cout, const float* w, const Epilogue& epi, int n_img,
                    cudaStream_t st) {
-    veclin_kernel<<<n_img, 128, cin * sizeof(float), st>>>(in, cin, out, cout, w, to_dev(epi));
+    pdl_launch(veclin_kernel, n_img, 128, cin * sizeof(float), st, in, cin, out, cout, w, to_dev(epi));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,6 +479,8 @@ void launch_veclin(const float* in, int cin, float* out, int cout, const float* 
 template <typename T>
 __global__ void __launch_bounds__(256) chscale_kernel(const T* in, int in_cs, T* out, int out_cs, int cvecs, const float* scale,
                                                      int scale_c, int residual, const ImgTab* tab) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int img = blockIdx.y;
     const ImgTab ti = tab[img];
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -487,8 +502,8 @@ void launch_chscale(const void* in, int in_cs, void* out, int out_cs, int c_pad,
                     int residual, const ImgTab* tab, int n_img, int max_pix, int prec, cudaStream_t st) {
     int cvecs = c_pad / 8;
     dim3 grid(cdiv(int64_t(max_pix) * cvecs, 256), n_img);
-    if (prec == 0) chscale_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, (__half*)out, out_cs, cvecs, scale, scale_c, residual, tab);
-    else chscale_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, (float*)out, out_cs, cvecs, scale, scale_c, residual, tab);
+    if (prec == 0) pdl_launch(chscale_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, (__half*)out, out_cs, cvecs, scale, scale_c, residual, tab);
+    else pdl_launch(chscale_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, (float*)out, out_cs, cvecs, scale, scale_c, residual, tab);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -498,6 +513,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) pool_kernel(const T* in, int in_cs, T* out, int out_cs, int cvecs, const ImgTab* tin,
                                                   const ImgTab* tout, int kh, int kw, int sh, int sw, int ph, int pw, int is_max,
                                                   int exclusive) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int img = blockIdx.y;
     const ImgTab ti = tin[img], to = tout[img];
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -542,8 +559,8 @@ void launch_pool(const void* in, int in_cs, void* out, int out_cs, int c_pad, co
                  int prec, cudaStream_t st) {
     int cvecs = c_pad / 8;
     dim3 grid(cdiv(int64_t(max_out_pix) * cvecs, 256), n_img);
-    if (prec == 0) pool_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, (__half*)out, out_cs, cvecs, tin, tout, kh, kw, sh, sw, ph, pw, is_max, exclusive);
-    else pool_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, (float*)out, out_cs, cvecs, tin, tout, kh, kw, sh, sw, ph, pw, is_max, exclusive);
+    if (prec == 0) pdl_launch(pool_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, (__half*)out, out_cs, cvecs, tin, tout, kh, kw, sh, sw, ph, pw, is_max, exclusive);
+    else pdl_launch(pool_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, (float*)out, out_cs, cvecs, tin, tout, kh, kw, sh, sw, ph, pw, is_max, exclusive);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -552,6 +569,8 @@ void launch_pool(const void* in, int in_cs, void* out, int out_cs, int c_pad, co
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_kernel(const T* in, int in_cs, const T* add, int add_cs, T* out, int out_cs,
                                                       int cvecs, const ImgTab* tin, const ImgTab* tout, int scale) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int img = blockIdx.y;
     const ImgTab ti = tin[img], to = tout[img];
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -577,8 +596,8 @@ void launch_upsample(const void* in, int in_cs, const void* add, int add_cs, voi
                      cudaStream_t st) {
     int cvecs = c_pad / 8;
     dim3 grid(cdiv(int64_t(max_out_pix) * cvecs, 256), n_img);
-    if (prec == 0) upsample_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, (const __half*)add, add_cs, (__half*)out, out_cs, cvecs, tin, tout, scale);
-    else upsample_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, (const float*)add, add_cs, (float*)out, out_cs, cvecs, tin, tout, scale);
+    if (prec == 0) pdl_launch(upsample_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, (const __half*)add, add_cs, (__half*)out, out_cs, cvecs, tin, tout, scale);
+    else pdl_launch(upsample_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, (const float*)add, add_cs, (float*)out, out_cs, cvecs, tin, tout, scale);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,6 +606,8 @@ void launch_upsample(const void* in, int in_cs, const void* add, int add_cs, voi
 template <typename T>
 __global__ void __launch_bounds__(256) add_kernel(const T* a, int a_cs, const T* b, int b_cs, void* out, int out_cs, int cvecs,
                                                  int c_real, int64_t pixels, int act, int out_f32) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= pixels * cvecs) return;
     const int cv = int(idx % cvecs);
@@ -610,14 +631,16 @@ void launch_add(const void* a, int a_cs, const void* b, int b_cs, void* out, int
                 int64_t pixels, int act, int out_f32, int prec, cudaStream_t st) {
     int cvecs = c_pad / 8;
     int grid = cdiv(pixels * cvecs, 256);
-    if (prec == 0) add_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a, a_cs, (const __half*)b, b_cs, out, out_cs, cvecs, c_real, pixels, act, out_f32);
-    else add_kernel<float><<<grid, 256, 0, st>>>((const float*)a, a_cs, (const float*)b, b_cs, out, out_cs, cvecs, c_real, pixels, act, out_f32);
+    if (prec == 0) pdl_launch(add_kernel<__half>, grid, 256, 0, st, (const __half*)a, a_cs, (const __half*)b, b_cs, out, out_cs, cvecs, c_real, pixels, act, out_f32);
+    else pdl_launch(add_kernel<float>, grid, 256, 0, st, (const float*)a, a_cs, (const float*)b, b_cs, out, out_cs, cvecs, c_real, pixels, act, out_f32);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) eltwise_kernel(const T* in, int in_cs, void* out, int out_cs, int cvecs, int c_real,
                                                      int64_t pixels, const float* scale, const float* shift, int act,
                                                      float hs_slope, float hs_offset, int out_f32) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= pixels * cvecs) return;
     const int cv = int(idx % cvecs);
@@ -645,12 +668,14 @@ void launch_eltwise(const void* in, int in_cs, void* out, int out_cs, int c_pad,
                     int prec, cudaStream_t st) {
     int cvecs = c_pad / 8;
     int grid = cdiv(pixels * cvecs, 256);
-    if (prec == 0) eltwise_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, out, out_cs, cvecs, c_real, pixels, scale, shift, act, hs_slope, hs_offset, out_f32);
-    else eltwise_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, out, out_cs, cvecs, c_real, pixels, scale, shift, act, hs_slope, hs_offset, out_f32);
+    if (prec == 0) pdl_launch(eltwise_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, out, out_cs, cvecs, c_real, pixels, scale, shift, act, hs_slope, hs_offset, out_f32);
+    else pdl_launch(eltwise_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, out, out_cs, cvecs, c_real, pixels, scale, shift, act, hs_slope, hs_offset, out_f32);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) copy_kernel(const T* in, int in_cs, T* out, int out_cs, int cvecs, int64_t pixels) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= pixels * cvecs) return;
     const int cv = int(idx % cvecs);
@@ -666,6 +691,8 @@ __global__ void __launch_bounds__(256) copy_kernel(const T* in, int in_cs, T* ou
 template <typename T>
 __global__ void __launch_bounds__(256) copy_unaligned_kernel(const T* in, int in_cs, T* out, int out_cs, int c, int c_fill,
                                                             int64_t pixels) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= pixels * c_fill) return;
     const int ch = int(idx % c_fill);
@@ -676,15 +703,15 @@ __global__ void __launch_bounds__(256) copy_unaligned_kernel(const T* in, int in
 void launch_copy_unaligned(const void* in, int in_cs, void* out, int out_cs, int c, int c_fill, int64_t pixels, int prec,
                            cudaStream_t st) {
     int grid = cdiv(pixels * c_fill, 256);
-    if (prec == 0) copy_unaligned_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, (__half*)out, out_cs, c, c_fill, pixels);
-    else copy_unaligned_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, (float*)out, out_cs, c, c_fill, pixels);
+    if (prec == 0) pdl_launch(copy_unaligned_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, (__half*)out, out_cs, c, c_fill, pixels);
+    else pdl_launch(copy_unaligned_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, (float*)out, out_cs, c, c_fill, pixels);
 }
 
 void launch_copy(const void* in, int in_cs, void* out, int out_cs, int c_pad, int64_t pixels, int prec, cudaStream_t st) {
     int cvecs = c_pad / 8;
     int grid = cdiv(pixels * cvecs, 256);
-    if (prec == 0) copy_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, (__half*)out, out_cs, cvecs, pixels);
-    else copy_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, (float*)out, out_cs, cvecs, pixels);
+    if (prec == 0) pdl_launch(copy_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, (__half*)out, out_cs, cvecs, pixels);
+    else pdl_launch(copy_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, (float*)out, out_cs, cvecs, pixels);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -693,6 +720,8 @@ void launch_copy(const void* in, int in_cs, void* out, int out_cs, int c_pad, in
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* in, int in_cs, T* out, int out_cs, int c, int64_t pixels,
                                                        const float* gamma, const float* beta, float eps) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int64_t row = int64_t(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5);
     if (row >= pixels) return;
     const int lane = threadIdx.x & 31;
@@ -719,8 +748,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* in, int in_cs, 
 void launch_layernorm(const void* in, int in_cs, void* out, int out_cs, int c, int64_t pixels, const float* gamma,
                       const float* beta, float eps, int prec, cudaStream_t st) {
     int grid = cdiv(pixels, 8);
-    if (prec == 0) layernorm_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, (__half*)out, out_cs, c, pixels, gamma, beta, eps);
-    else layernorm_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, (float*)out, out_cs, c, pixels, gamma, beta, eps);
+    if (prec == 0) pdl_launch(layernorm_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, (__half*)out, out_cs, c, pixels, gamma, beta, eps);
+    else pdl_launch(layernorm_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, (float*)out, out_cs, c, pixels, gamma, beta, eps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -732,6 +761,8 @@ int attention_smem_bytes(int max_t, int dim) { return (2 * max_t * dim + 8 * max
 template <typename T>
 __global__ void __launch_bounds__(256) attention_kernel(const T* qkv, int qkv_cs, T* out, int out_cs, int heads, int dim,
                                                        float qscale, const ImgTab* tab) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     extern __shared__ float sm[];
     const int img = blockIdx.z, head = blockIdx.y;
     const ImgTab ti = tab[img];
@@ -790,10 +821,10 @@ void launch_attention(const void* qkv, int qkv_cs, void* out, int out_cs, int he
     dim3 grid(cdiv(max_t, 32), heads, n_img);
     if (prec == 0) {
         cudaFuncSetAttribute(attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attention_kernel<__half><<<grid, 256, smem, st>>>((const __half*)qkv, qkv_cs, (__half*)out, out_cs, heads, dim, qscale, tab);
+        pdl_launch(attention_kernel<__half>, grid, 256, smem, st, (const __half*)qkv, qkv_cs, (__half*)out, out_cs, heads, dim, qscale, tab);
     } else {
         cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attention_kernel<float><<<grid, 256, smem, st>>>((const float*)qkv, qkv_cs, (float*)out, out_cs, heads, dim, qscale, tab);
+        pdl_launch(attention_kernel<float>, grid, 256, smem, st, (const float*)qkv, qkv_cs, (float*)out, out_cs, heads, dim, qscale, tab);
     }
 }
 
@@ -802,6 +833,8 @@ void launch_attention(const void* qkv, int qkv_cs, void* out, int out_cs, int he
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) softmax_kernel(const T* in, int in_cs, float* out, int c, int64_t pixels) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     __shared__ float red[4];
     const int64_t row = blockIdx.x;
     const T* x = in + size_t(row) * in_cs;
@@ -828,8 +861,8 @@ __global__ void __launch_bounds__(128) softmax_kernel(const T* in, int in_cs, fl
 
 void launch_softmax(const void* in, int in_cs, float* out, int c, int64_t pixels, int prec, cudaStream_t st) {
     if (pixels <= 0) return;
-    if (prec == 0) softmax_kernel<__half><<<(unsigned)pixels, 128, 0, st>>>((const __half*)in, in_cs, out, c, pixels);
-    else softmax_kernel<float><<<(unsigned)pixels, 128, 0, st>>>((const float*)in, in_cs, out, c, pixels);
+    if (prec == 0) pdl_launch(softmax_kernel<__half>, (unsigned)pixels, 128, 0, st, (const __half*)in, in_cs, out, c, pixels);
+    else pdl_launch(softmax_kernel<float>, (unsigned)pixels, 128, 0, st, (const float*)in, in_cs, out, c, pixels);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -837,6 +870,8 @@ void launch_softmax(const void* in, int in_cs, float* out, int c, int64_t pixels
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void to_float_kernel(const T* in, int in_cs, float* out, int c, int64_t pixels) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= pixels * c) return;
     const int64_t pix = idx / c;
@@ -848,8 +883,8 @@ void launch_to_float(const void* in, int in_cs, int dtype_is_f32, float* out, in
                      cudaStream_t st) {
     if (pixels * c <= 0) return;
     int grid = cdiv(pixels * c, 256);
-    if (dtype_is_f32 || prec == 1) to_float_kernel<float><<<grid, 256, 0, st>>>((const float*)in, in_cs, out, c, pixels);
-    else to_float_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, in_cs, out, c, pixels);
+    if (dtype_is_f32 || prec == 1) pdl_launch(to_float_kernel<float>, grid, 256, 0, st, (const float*)in, in_cs, out, c, pixels);
+    else pdl_launch(to_float_kernel<__half>, grid, 256, 0, st, (const __half*)in, in_cs, out, c, pixels);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -859,6 +894,8 @@ void launch_to_float(const void* in, int in_cs, int dtype_is_f32, float* out, in
 // ------------------------------------------------------------------------------------------------
 struct UploadBlob { uint32_t w[1000]; };
 __global__ void upload_kernel(UploadBlob b, uint32_t* dst, int nwords) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = b.w[i];
 }
 
@@ -870,7 +907,7 @@ int launch_upload(void* dst, const void* src_host, size_t bytes, cudaStream_t st
         const size_t m = bytes - off < chunk ? bytes - off : chunk;
         std::memcpy(b.w, static_cast<const char*>(src_host) + off, m);
         // destination buffers are DevBuf allocations (256-byte slack): rounding the tail up to 4 bytes stays inside
-        upload_kernel<<<1, 256, 0, st>>>(b, reinterpret_cast<uint32_t*>(static_cast<char*>(dst) + off), int((m + 3) / 4));
+        pdl_launch(upload_kernel, 1, 256, 0, st, b, reinterpret_cast<uint32_t*>(static_cast<char*>(dst) + off), int((m + 3) / 4));
     }
     return n;
 }

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "dbpost_core.cuh"
+#include "pdl.cuh"
 #include "engine.h"
 #include "postproc.cuh"
 #include "preproc.cuh"
@@ -316,7 +317,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         std::memcpy(P->h_in.p, jobs.data(), n * sizeof(ResizeJob));
         launch_upload(P->jobs.p, P->h_in.p, n * sizeof(ResizeJob), stream);   // (kernel parameters: h_in is free again)
         dim3 grid((max_pix + 255) / 256, n);
-        resize_bilinear_u8_kernel<<<grid, 256, 0, stream>>>(P->jobs.as<ResizeJob>(), P->det_in.as<uint8_t>(), max_pix);
+        pdl_launch(resize_bilinear_u8_kernel, grid, 256, 0, stream, P->jobs.as<ResizeJob>(), P->det_in.as<uint8_t>(), max_pix);
         launches++;
         VSE_CUDA(cudaGetLastError());
     }
@@ -468,7 +469,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
             launches++;
         }
         dim3 grid((max_rec_pix + 255) / 256, nC);
-        resize_bilinear_u8_kernel<<<grid, 256, 0, stream>>>(P->rec_jobs.as<ResizeJob>(), P->rec_in.as<uint8_t>(), max_rec_pix);
+        pdl_launch(resize_bilinear_u8_kernel, grid, 256, 0, stream, P->rec_jobs.as<ResizeJob>(), P->rec_in.as<uint8_t>(), max_rec_pix);
         launches++;
         VSE_CUDA(cudaGetLastError());
         VSE_CUDA(cudaStreamSynchronize(stream));  // h_in is reused by run_plan's table upload
@@ -560,7 +561,7 @@ void Engine::debug_resize(const uint8_t* src, int sh, int sw, int stride, uint8_
     ResizeJob j{pipe_->dbg_frames.as<uint8_t>(), sh, sw, stride, 3, dh, dw, dw, 0};
     VSE_CUDA(cudaMemcpyAsync(pipe_->jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice, stream));
     dim3 grid((dh * dw + 255) / 256, 1);
-    resize_bilinear_u8_kernel<<<grid, 256, 0, stream>>>(pipe_->jobs.as<ResizeJob>(), pipe_->det_in.as<uint8_t>(), dh * dw);
+    pdl_launch(resize_bilinear_u8_kernel, grid, 256, 0, stream, pipe_->jobs.as<ResizeJob>(), pipe_->det_in.as<uint8_t>(), dh * dw);
     launches++;
     VSE_CUDA(cudaGetLastError());
     VSE_CUDA(cudaMemcpyAsync(dst, pipe_->det_in.p, size_t(dh) * dw * 4, cudaMemcpyDeviceToHost, stream));

@@ -11,6 +11,7 @@
 // Scope note: cv2.findContours(RETR_LIST) also reports hole borders; a hole contour only survives upstream when its
 // own box scores >= 0.6 and is >= 5 px after unclip.  Holes are not traced here (documented in DESIGN.md).
 #include "postproc.cuh"
+#include "pdl.cuh"
 
 #include <cfloat>
 
@@ -54,6 +55,8 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ prob, const DetFrame* __restrict__ frames,
                                                      float thresh, int* __restrict__ labels, int* __restrict__ status,
                                                      int* __restrict__ fg_count, int* __restrict__ fg_list) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const DetFrame fr = frames[blockIdx.z];
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const bool in = x < fr.rw && y < fr.rh;
@@ -86,6 +89,8 @@ __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ p
 
 __global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict__ frames, int* labels,
                                                       const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
   const int n_fg = *fg_count;
   for (int it = blockIdx.x; it < n_fg; it += gridDim.x) {
     const int code = fg_list[it], bz = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
@@ -117,6 +122,8 @@ __global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict
 __global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restrict__ frames, int* labels, int* slot_of,
                                                         int* n_comp, int* roots, int* bbox,
                                                         const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
   const int n_fg = *fg_count;
   for (int it = blockIdx.x; it < n_fg; it += gridDim.x) {
     const int code = fg_list[it], f = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
@@ -144,6 +151,8 @@ __global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restri
 __global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ frames, const int* __restrict__ labels,
                                                const int* __restrict__ slot_of, int* bbox,
                                                const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
   const int n_fg = *fg_count;
   for (int it = blockIdx.x; it < n_fg; it += gridDim.x) {
     const int code = fg_list[it], f = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
@@ -171,6 +180,8 @@ __global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ fram
 // cv2.findContours(RETR_LIST) returns contours in reverse discovery order: descending root (raster) index
 __global__ void __launch_bounds__(256) db_sort_components(const int* __restrict__ n_comp, const int* __restrict__ roots,
                                                           int* order, int* status) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int f = blockIdx.x;
     int n = n_comp[f];
     if (n > kSlotCap) {
@@ -201,6 +212,8 @@ __global__ void __launch_bounds__(kCandThreads) db_candidates(const float* __res
                                                               const int* __restrict__ labels, const int* __restrict__ n_comp,
                                                               const int* __restrict__ roots, const int* __restrict__ bbox,
                                                               const int* __restrict__ order, DbParams p, int max_rh, float* cand) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char smem[];
     int* xl = reinterpret_cast<int*>(smem);
     int* xr = xl + max_rh;
@@ -286,6 +299,8 @@ __global__ void __launch_bounds__(kCandThreads) db_candidates(const float* __res
 // keep valid candidates in contour order, optionally re-order like TextSystem.sorted_boxes
 __global__ void db_compact(const int* __restrict__ n_comp, const float* __restrict__ cand, DbParams p, int* n_boxes,
                            float* quads, float* scores, int* status) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const int f = blockIdx.x;
     if (threadIdx.x != 0) return;
     int n = min(min(n_comp[f], kSlotCap), p.max_candidates);
@@ -344,21 +359,21 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
     // machine-sized grid (subtitle maps are > 99 % background, and launching 65 k empty blocks costs more than the work)
     if (grid.x > 1023 || grid.y > 1023 || n_frames > 2047) return;   // list code = frame << 20 | block_y << 10 | block_x (checked by the caller)
     cudaMemsetAsync(ws.fg_count, 0, sizeof(int), st);
-    db_label_init<<<grid, blk, 0, st>>>(prob, frames_dev, p.thresh, ws.labels, ws.status, ws.fg_count, ws.fg_list);
+    pdl_launch(db_label_init, grid, blk, 0, st, prob, frames_dev, p.thresh, ws.labels, ws.status, ws.fg_count, ws.fg_list);
     const int pgrid = 148 * 4;
-    db_label_merge<<<pgrid, blk, 0, st>>>(frames_dev, ws.labels, ws.fg_count, ws.fg_list);
-    db_label_flatten<<<pgrid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox, ws.fg_count, ws.fg_list);
-    db_bbox<<<pgrid, blk, 0, st>>>(frames_dev, ws.labels, ws.slot_of, ws.bbox, ws.fg_count, ws.fg_list);
-    db_sort_components<<<n_frames, 256, 0, st>>>(ws.n_comp, ws.roots, ws.order, ws.status);
+    pdl_launch(db_label_merge, pgrid, blk, 0, st, frames_dev, ws.labels, ws.fg_count, ws.fg_list);
+    pdl_launch(db_label_flatten, pgrid, blk, 0, st, frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox, ws.fg_count, ws.fg_list);
+    pdl_launch(db_bbox, pgrid, blk, 0, st, frames_dev, ws.labels, ws.slot_of, ws.bbox, ws.fg_count, ws.fg_list);
+    pdl_launch(db_sort_components, n_frames, 256, 0, st, ws.n_comp, ws.roots, ws.order, ws.status);
     size_t smem = db_candidate_smem_bytes(max_rh);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(db_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    db_candidates<<<dim3(16, n_frames), kCandThreads, smem, st>>>(prob, frames_dev, ws.labels, ws.n_comp, ws.roots, ws.bbox,
+    pdl_launch(db_candidates, dim3(16, n_frames), kCandThreads, smem, st, prob, frames_dev, ws.labels, ws.n_comp, ws.roots, ws.bbox,
                                                                   ws.order, p, max_rh, ws.cand);
-    db_compact<<<n_frames, 32, 0, st>>>(ws.n_comp, ws.cand, p, ws.n_boxes, ws.quads, ws.scores, ws.status);
+    pdl_launch(db_compact, n_frames, 32, 0, st, ws.n_comp, ws.cand, p, ws.n_boxes, ws.quads, ws.scores, ws.status);
     if (launches) *launches += 7;
 }
 
@@ -367,6 +382,8 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) crop_warp_kernel(const CropJob* __restrict__ jobs, const short* __restrict__ tab,
                                                         uint8_t* __restrict__ dst) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const CropJob& j = jobs[blockIdx.y];
     const int ow = j.rot90 ? j.ch : j.cw, oh = j.rot90 ? j.cw : j.ch;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,7 +400,7 @@ __global__ void __launch_bounds__(256) crop_warp_kernel(const CropJob* __restric
 void launch_crops(const CropJob* jobs_dev, int n_jobs, int max_pix, const short* cubic_tab, uint8_t* dst, cudaStream_t st) {
     if (n_jobs <= 0 || max_pix <= 0) return;
     dim3 grid((max_pix + 255) / 256, n_jobs);
-    crop_warp_kernel<<<grid, 256, 0, st>>>(jobs_dev, cubic_tab, dst);
+    pdl_launch(crop_warp_kernel, grid, 256, 0, st, jobs_dev, cubic_tab, dst);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,6 +409,8 @@ void launch_crops(const CropJob* jobs_dev, int n_jobs, int max_pix, const short*
 __global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict__ probs, int C, const int* __restrict__ toff,
                                                          const int* __restrict__ tlen, int max_t, int* __restrict__ ids,
                                                          int* __restrict__ id_len, float* __restrict__ score) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     extern __shared__ __align__(8) unsigned char sm[];
     int* bi = reinterpret_cast<int*>(sm);
     float* bp = reinterpret_cast<float*>(bi + max_t);
@@ -443,7 +462,7 @@ void launch_ctc_decode(const float* probs, int C, const int* toff, const int* tl
         cudaFuncSetAttribute(ctc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    ctc_decode_kernel<<<n, 128, smem, st>>>(probs, C, toff, tlen, max_t, ids, id_len, score);
+    pdl_launch(ctc_decode_kernel, n, 128, smem, st, probs, C, toff, tlen, max_t, ids, id_len, score);
 }
 
 }  // namespace vse

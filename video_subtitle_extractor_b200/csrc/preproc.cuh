@@ -7,6 +7,7 @@
 // Checked bit-exact against cv2 4.13 in tests/test_gpu_parity.py (and the numpy restatement in tests/test_host_cpu.py).
 #pragma once
 #include <cuda_runtime.h>
+#include "pdl.cuh"
 #include <cstdint>
 
 namespace vse {
@@ -37,6 +38,8 @@ __device__ __forceinline__ void resize_coeff(int d, int dn, int sn, bool clamp_e
 
 // one thread per destination pixel; writes BGRX (X = 0)
 __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const ResizeJob* jobs, uint8_t* dst, int max_pix) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
     const ResizeJob j = jobs[blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= j.dst_h * j.dst_w) return;
