@@ -208,7 +208,9 @@ def step_roofline(eng, E):
             elif op == P.OP_STEM:
                 kname = "stem_fast_kernel" if kind == 2 else "conv_simt_kernel"
             elif op == P.OP_DWCONV:
-                kname = "dwconv_fast_kernel" if kind == 2 else "dwconv_kernel"
+                # the engine's default depthwise family is the register-tiled kernel (engine.cu, VSE_DW_MODE switches it)
+                dw_fast = {"0": "dwconv_fast_kernel", "1": "dwconv_tile_kernel"}.get(os.environ.get("VSE_DW_MODE", "2"), "dwconv_reg_kernel")
+                kname = dw_fast if kind == 2 else "dwconv_kernel"
             elif op == P.OP_DECONV2:
                 kname = "db_head_fused_kernel" if kind == 2 else "deconv2_kernel"
             else:

@@ -366,16 +366,32 @@ __device__ __forceinline__ float2 fact2(float2 v) {
 
 template <int K, int SH, int SW, int TH, int TW, int ACT>
 __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x, int tiles_y) {
-    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
-    pdl_trigger();
     constexpr int IH = (TH - 1) * SH + K, IW = (TW - 1) * SW + K;
     const int img = blockIdx.y;
-    const ImgTab ti = p.tin[img], to = p.tout[img];
     const int cp2 = p.cvecs * 4;                          // channel pairs per pixel
     const unsigned idx = blockIdx.x * 128u + threadIdx.x;   // the launcher keeps tiles * pairs below 2^31
     const unsigned tile = idx / unsigned(cp2);
     const int pair = int(idx - tile * unsigned(cp2));
     if (tile >= unsigned(tiles_x * tiles_y)) return;
+    // filter, bias and post-affine of this channel pair are static weights: loaded BEFORE the dependency wait, so under
+    // programmatic dependent launch (pdl.cuh) this round trip overlaps the tail of the previous step's kernel
+    float2 w[K * K];
+    {
+        const char* wp = reinterpret_cast<const char*>(p.w + pair * 2);
+        const unsigned wstep = unsigned(p.cp) * 4u;
+#pragma unroll
+        for (int t = 0; t < K * K; t++) w[t] = __ldg(reinterpret_cast<const float2*>(addr_mad(wp, unsigned(t), wstep)));
+    }
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + pair * 2));
+    const bool post = p.ps != nullptr;
+    float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+    if (post) {
+        sc = __ldg(reinterpret_cast<const float2*>(p.ps + pair * 2));
+        sh = __ldg(reinterpret_cast<const float2*>(p.pt + pair * 2));
+    }
+    pdl_wait();      // image tables and activations come from earlier kernels of the stream
+    pdl_trigger();
+    const ImgTab ti = p.tin[img], to = p.tout[img];
     const int ty = int(tile / unsigned(tiles_x)), tx = int(tile) - ty * tiles_x;
     const int oy0 = ty * TH, ox0 = tx * TW;
     if (oy0 >= to.h || ox0 >= to.w) return;
@@ -413,13 +429,6 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
             }
         }
     }
-    float2 w[K * K];
-    {
-        const char* wp = reinterpret_cast<const char*>(p.w + c0);
-        const unsigned wstep = unsigned(p.cp) * 4u;
-#pragma unroll
-        for (int t = 0; t < K * K; t++) w[t] = __ldg(reinterpret_cast<const float2*>(addr_mad(wp, unsigned(t), wstep)));
-    }
     float2 acc[TH][TW];
 #pragma unroll
     for (int a = 0; a < TH; a++)
@@ -443,13 +452,6 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
                 }
             }
         }
-    }
-    const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
-    const bool post = p.ps != nullptr;
-    float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
-    if (post) {
-        sc = __ldg(reinterpret_cast<const float2*>(p.ps + c0));
-        sh = __ldg(reinterpret_cast<const float2*>(p.pt + c0));
     }
     char* obase = reinterpret_cast<char*>(p.out + (size_t(to.off) + size_t(oy0) * to.w + ox0) * p.out_cs + c0);
     const unsigned ocstep = unsigned(p.out_cs) * 2u, orstep = unsigned(to.w) * ocstep;
@@ -499,7 +501,7 @@ bool launch_dwconv_reg(const ConvArgs& a, int max_out_h, int max_out_w, cudaStre
         case 321: return VSE_DW_REG(3, 2, 1);
         case 312: return VSE_DW_REG(3, 1, 2);
         case 511: return VSE_DW_REG(5, 1, 1);
-        case 522: return VSE_DW_REG(5, 2, 2);
+        case 522: return dw_reg_launch<5, 2, 2, 2, 4>(d, a, max_out_h, max_out_w, st);   // 7 x 11 patch: the 4-row tile (11 x 11) would spill
         case 521: return VSE_DW_REG(5, 2, 1);
         case 512: return VSE_DW_REG(5, 1, 2);
         default: return false;
