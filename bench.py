@@ -213,6 +213,8 @@ def step_roofline(eng, E):
                 kname = dw_fast if kind == 2 else "dwconv_kernel"
             elif op == P.OP_DECONV2:
                 kname = "db_head_fused_kernel" if kind == 2 else "deconv2_kernel"
+            elif op == P.OP_LSTM:
+                kname = "lstm_recurrent_kernel"
             else:
                 kname = name.lower() + "_kernel"
             rows.append((which, kname, float(t), bytes_, flops))
@@ -292,7 +294,9 @@ def run_b200(args, rank, local_rank, world):
         dev_batches.append(pinned.to(dev))
     torch.cuda.synchronize()
 
-    eng = E.Engine(device=local_rank, precision=E.PRECISION_FP16, flags=args.flags)
+    # V2 recognisers (ResNet + BiLSTM) read 32-pixel-high crops (reference backend/tools/paddle_model_config.py:94-97)
+    rec_h = 32 if REC.startswith("V2/") else 48
+    eng = E.Engine(device=local_rank, precision=E.PRECISION_FP16, flags=args.flags, rec_image_h=rec_h)
     eng.load_plan(E.PLAN_DET, det_blob, DET)
     eng.load_plan(E.PLAN_REC, rec_blob, REC)
     hs, ws = [H] * B, [W] * B

@@ -509,6 +509,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
 
     // tensor-core plans (need the final arena addresses for the TMA descriptors)
     cx.tc.assign(pd.steps.size(), TcConv{});
+    cx.tc_groups.assign(pd.steps.size(), {});
     for (size_t k = 0; k < pd.steps.size() && !keep_all_disables_tc(keep_all); k++) {
         const StepRec& s = pd.steps[k];
         if (s.op != OP_CONV || lp.tcw[k].n_chunk == 0) continue;
@@ -519,6 +520,28 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         const bool flat = kh == 1 && kw == 1 && ph == 0 && pw == 0;
         bool uniform = true;
         for (auto& t : gi.tab) uniform = uniform && t.h == gi.tab[0].h && t.w == gi.tab[0].w;
+        if (!flat && !uniform && 2 * ph == kh - 1 && 2 * pw == kw - 1 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
+            // ragged batch: one launch per run of equal-sized images (see ExecContext::tc_groups); all groups or none
+            const size_t es = plan_prec_[which] == VSE_PRECISION_FP16 ? 2 : 4;
+            const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_off[k];
+            std::vector<ExecContext::TcGroup> groups;
+            bool ok = true;
+            for (size_t i0 = 0; i0 < gi.tab.size() && ok;) {
+                size_t i1 = i0 + 1;
+                while (i1 < gi.tab.size() && gi.tab[i1].h == gi.tab[i0].h && gi.tab[i1].w == gi.tab[i0].w) i1++;
+                ExecContext::TcGroup g;
+                g.pix_off = gi.tab[i0].off;
+                const char* base = static_cast<const char*>(vptr(which, s.ins[0])) + size_t(g.pix_off) * value_cs(pd, s.ins[0]) * es;
+                const int64_t gpix = int64_t(i1 - i0) * gi.tab[i0].h * gi.tab[i0].w;
+                ok = tc_conv_setup(g.tc, base, value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], false, gpix, int(i1 - i0), gi.tab[i0].h,
+                                   gi.tab[i0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX), !(cfg.flags & VSE_FLAG_NO_HALO)).empty();
+                groups.push_back(std::move(g));
+                i0 = i1;
+                if (groups.size() > 64) ok = false;
+            }
+            if (ok) cx.tc_groups[k] = std::move(groups);
+            continue;
+        }
         if (!flat && !(uniform && 2 * ph == kh - 1 && 2 * pw == kw - 1)) continue;
         if (flat && lp.dev[k].pack > 0 && lp.tcw_pk[k].n_chunk > 0 && gi.total % lp.dev[k].pack == 0) {
             // pixel-packed: `pack` pixels per GEMM row, K = 64, block-diagonal weights
@@ -944,6 +967,29 @@ int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
 
 bool Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
     TcConv& t = ctx_[which].tc[step];
+    auto& groups = ctx_[which].tc_groups[step];
+    if (!groups.empty()) {   // ragged KxK convolution: one tensor-core launch per run of equal-sized images
+        const size_t es = plan_prec_[which] == VSE_PRECISION_FP16 ? 2 : 4;
+        bool ok = true;
+        size_t done = 0;
+        for (auto& g : groups) {
+            TcConv& tg = g.tc;
+            tg.out = static_cast<char*>(a.out) + size_t(g.pix_off) * a.out_cs * es;   // same-padding stride 1: output pixels = input pixels
+            tg.out_cs = a.out_cs;
+            tg.n_store = a.cout_store;
+            tg.epi = a.epi;
+            if (a.epi.res) tg.epi.res = static_cast<const char*>(a.epi.res) + size_t(g.pix_off) * a.epi.res_cs * es;
+            if (!launch_conv_tc(tg, sm_count, stream).empty()) { ok = false; break; }
+            done++;
+        }
+        if (ok) {
+            tc_launches += int64_t(groups.size());
+            launches += int64_t(groups.size()) - 1;
+            return true;
+        }
+        if (done > 0) throw StateError{"ragged tensor-core convolution failed after launching part of its groups"};
+        groups.clear();   // e.g. an output view the TMA store cannot address: CUDA-core kernel from now on
+    }
     (void)prec;
     if (t.valid) {   // built only for plans whose precision uses the tensor cores (fp16 / tf32)
         t.out = a.out;

@@ -133,6 +133,14 @@ struct ExecContext {
     size_t scratch_off = 0, scratch_bytes = 0;
     int n_img = 0;
     std::vector<TcConv> tc;   // per step; valid => the step runs on the tcgen05 kernel for this geometry
+    // KxK convolutions over a RAGGED batch (recogniser crops of different padded widths): one tensor-core launch per run
+    // of consecutive equal-sized images (the reference pads every <= 6-crop batch to one width, so a ragged batch is a
+    // short list of uniform groups).  Non-empty => the step runs as these launches.
+    struct TcGroup {
+        TcConv tc;
+        int64_t pix_off = 0;   // first pixel of the group in the step's input / output / residual values
+    };
+    std::vector<std::vector<TcGroup>> tc_groups;
     std::vector<char> se_conv; // per step: 1 = 1x1 conv heading a fused residual squeeze-excite group (build_context)
     std::vector<int> kind;    // per step, filled by exec_steps: which kernel family ran (see Engine::time_steps)
 };
