@@ -468,8 +468,71 @@ __global__ void veclin_kernel(const float* in, int cin, float* out, int cout, co
     }
 }
 
+// Wide layers (the server models' squeeze-excite FCs, up to 2048 x 2048): one warp = NO output channels x NI images, the
+// weight rows are read as coalesced float4 (once per NI images instead of once per image by one strided thread), the
+// input vectors come from L1/L2, and the lanes' partial sums meet in a shuffle tree.
+template <int NO, int NI>
+__global__ void __launch_bounds__(256) veclin_warp_kernel(const float* __restrict__ in, int cin, float* __restrict__ out, int cout,
+                                                          const float* __restrict__ w, EpiDev e, int n_img) {
+    pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
+    pdl_trigger();
+    const int lane = threadIdx.x & 31;
+    const int co0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * NO, i0 = blockIdx.y * NI;
+    if (co0 >= cout) return;
+    float acc[NO][NI];
+#pragma unroll
+    for (int o = 0; o < NO; o++)
+#pragma unroll
+        for (int i = 0; i < NI; i++) acc[o][i] = 0.f;
+    for (int k = lane * 4; k < cin; k += 128) {
+        float4 wv[NO], xv[NI];
+#pragma unroll
+        for (int o = 0; o < NO; o++)
+            wv[o] = co0 + o < cout ? __ldg(reinterpret_cast<const float4*>(w + size_t(co0 + o) * cin + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+            xv[i] = i0 + i < n_img ? *reinterpret_cast<const float4*>(in + size_t(i0 + i) * cin + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < NO; o++)
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                acc[o][i] = fmaf(wv[o].x, xv[i].x, acc[o][i]);
+                acc[o][i] = fmaf(wv[o].y, xv[i].y, acc[o][i]);
+                acc[o][i] = fmaf(wv[o].z, xv[i].z, acc[o][i]);
+                acc[o][i] = fmaf(wv[o].w, xv[i].w, acc[o][i]);
+            }
+    }
+#pragma unroll
+    for (int o = 0; o < NO; o++)
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc[o][i] += __shfl_xor_sync(0xffffffffu, acc[o][i], off);
+    if (lane == 0) {
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
+            const int co = co0 + o;
+            if (co >= cout) break;
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                if (i0 + i >= n_img) break;
+                float v = acc[o][i] + (e.bias ? e.bias[co] : 0.f);
+                v = act_apply(v, e.act, e.hs_slope, e.hs_offset);
+                if (e.post_scale) v = v * e.post_scale[co] + e.post_shift[co];
+                out[size_t(i0 + i) * cout + co] = act_apply(v, e.act2, 0.f, 0.f);
+            }
+        }
+    }
+}
+
 void launch_veclin(const float* in, int cin, float* out, int cout, const float* w, const Epilogue& epi, int n_img,
                    cudaStream_t st) {
+    if (cin >= 128 && cin % 4 == 0 && !(reinterpret_cast<uintptr_t>(w) & 15) && !(reinterpret_cast<uintptr_t>(in) & 15)) {
+        constexpr int NO = 4, NI = 4;
+        dim3 grid(cdiv(cout, NO * 8), cdiv(n_img, NI));
+        pdl_launch(veclin_warp_kernel<NO, NI>, grid, 256, 0, st, in, cin, out, cout, w, to_dev(epi), n_img);
+        return;
+    }
     pdl_launch(veclin_kernel, n_img, 128, cin * sizeof(float), st, in, cin, out, cout, w, to_dev(epi));
 }
 
