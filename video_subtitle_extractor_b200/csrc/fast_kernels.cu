@@ -47,6 +47,29 @@ __device__ __forceinline__ float fact(float x) {
     else return x;
 }
 
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE fp32 operations per issued instruction, each lane
+// rounded exactly like the scalar instruction) and a one-instruction 64-bit address  base + a * b  (IMAD.WIDE.U32)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ const char* addr_mad(const char* base, unsigned a, unsigned b) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(reinterpret_cast<unsigned long long>(base)));
+    return reinterpret_cast<const char*>(d);
+}
 // ------------------------------------------------------------------------------------------------
 // depthwise KxK
 // ------------------------------------------------------------------------------------------------
@@ -331,29 +354,6 @@ bool launch_dwconv_tiled(const ConvArgs& a, int max_out_h, int max_out_w, cudaSt
 // Accumulation order per output (ky, then kx ascending, fp32 fmaf from 0) is the same as in the other depthwise kernels,
 // so the results are bit-identical to theirs.
 // ------------------------------------------------------------------------------------------------
-// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE fp32 operations per issued instruction, each lane
-// rounded exactly like the scalar instruction) and a one-instruction 64-bit address  base + a * b  (IMAD.WIDE.U32)
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
-    return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ const char* addr_mad(const char* base, unsigned a, unsigned b) {
-    unsigned long long d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(reinterpret_cast<unsigned long long>(base)));
-    return reinterpret_cast<const char*>(d);
-}
 template <int ACT>
 __device__ __forceinline__ float2 fact2(float2 v) {
     if constexpr (ACT == ACT_RELU) return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
@@ -536,11 +536,12 @@ __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= to.h * pairs) return;
     const int oy = idx / pairs, ox0 = (idx - oy * pairs) * 2;
-    float acc[2][16];
+    // accumulators as channel pairs: one FFMA2 (fma.rn.f32x2) per two output channels, each lane rounded like the scalar FMA
+    float2 acc[2][8];
 #pragma unroll
     for (int t = 0; t < 2; t++)
 #pragma unroll
-        for (int j = 0; j < 16; j++) acc[t][j] = sb[j];
+        for (int j = 0; j < 8; j++) acc[t][j] = make_float2(sb[2 * j], sb[2 * j + 1]);
     const int iy0 = oy * 2 - 1, ix0 = ox0 * 2 - 1;
 #pragma unroll
     for (int ky = 0; ky < 3; ky++) {
@@ -565,17 +566,19 @@ __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
 #pragma unroll
             for (int ci = 0; ci < 3; ci++) {
                 const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * 16);
-                float w[16];
+                float2 w[8];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const float4 f = wp[q];
-                    w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+                    w[2 * q] = make_float2(f.x, f.y);
+                    w[2 * q + 1] = make_float2(f.z, f.w);
                 }
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
                     const float x = px[kx + 2 * t][ci];
+                    const float2 xx = make_float2(x, x);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) acc[t][j] = fmaf(x, w[j], acc[t][j]);
+                    for (int j = 0; j < 8; j++) acc[t][j] = ffma2(xx, w[j], acc[t][j]);
                 }
             }
         }
@@ -586,7 +589,10 @@ __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
         if (ox >= to.w) break;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = fact<ACT>(acc[t][j]);
+        for (int j = 0; j < 8; j++) {
+            v[2 * j] = fact<ACT>(acc[t][j].x);
+            v[2 * j + 1] = fact<ACT>(acc[t][j].y);
+        }
         __half* o = p.out + (size_t(to.off) + size_t(oy) * to.w + ox) * p.out_cs;
         store8h(o, v);
         store8h(o + 8, v + 8);
@@ -644,15 +650,17 @@ __global__ void __launch_bounds__(128, 4) db_head_fused_kernel(HeadDev p) {
         float mid[C];
 #pragma unroll
         for (int co = 0; co < C; co++) {
+            // packed fp32x2 FMAs (FFMA2) over input-channel pairs: even channels accumulate in .x (starting from the
+            // bias), odd channels in .y, summed at the end — half the FMA issue slots of the scalar chain
             const float4* wr = reinterpret_cast<const float4*>(sw1 + (pos1 * C + co) * C);
-            float m = sb1[co];
+            float2 m = make_float2(sb1[co], 0.f);
 #pragma unroll
             for (int q = 0; q < C / 4; q++) {
                 const float4 w = wr[q];
-                m = fmaf(x[4 * q], w.x, m); m = fmaf(x[4 * q + 1], w.y, m);
-                m = fmaf(x[4 * q + 2], w.z, m); m = fmaf(x[4 * q + 3], w.w, m);
+                m = ffma2(make_float2(x[4 * q], x[4 * q + 1]), make_float2(w.x, w.y), m);
+                m = ffma2(make_float2(x[4 * q + 2], x[4 * q + 3]), make_float2(w.z, w.w), m);
             }
-            mid[co] = fmaxf(m, 0.f);
+            mid[co] = fmaxf(m.x + m.y, 0.f);
         }
 #pragma unroll
         for (int pos2 = 0; pos2 < 4; pos2++) {
