@@ -276,39 +276,70 @@ __device__ __forceinline__ float tc_act(float x, int act, float slope, float off
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// 16 accumulator columns of one output pixel -> 16 output values: fp16 (two 16-byte pieces) or fp32 (four pieces)
-template <int ACT, bool POST, bool OUTF32>
-__device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* raw, const float* pb, const float* ps,
-                                            const float* pt, int cb, long long pix, uint4* out4, const float* grow) {
+// What the epilogue needs from TcParams, read ONCE into registers by epilogue_loop (TcParams lives in local memory once
+// it is passed by reference into the non-inlined loops: every p.field inside the column loop was a local-memory load).
+struct EpiRegs {
+    const float *pb, *ps, *pt;     // per-channel bias / post scale / post shift (generic pointers: global or shared)
+    uint32_t pb_s, ps_s, pt_s;     // the same as shared-memory addresses when they are staged there (PSM)
+    const void* res;
+    int res_cs, n_store, act, act2, gate_c;
+    float hs_slope, hs_offset;
+};
+
+// per-channel constants: PSM = staged in shared memory -> ld.shared (the generic loads the compiler has to emit for a
+// pointer that may be global or shared cost a descriptor set-up per load on top of the load)
+template <bool PSM>
+__device__ __forceinline__ float4 ld_const4(const float* g, uint32_t s_addr, int idx) {
+    if constexpr (PSM) {
+        float4 v;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(s_addr + uint32_t(idx) * 4u));
+        return v;
+    } else {
+        return ld4(g + idx);
+    }
+}
+
+// 16 accumulator columns of one output pixel -> 16 output values: fp16 (two 16-byte pieces) or fp32 (four pieces).
+// ACT < 0: activation kind read at run time (the rare layers whose constants do not fit shared memory).
+template <int ACT, bool POST, bool OUTF32, bool PSM, bool GATE>
+__device__ __forceinline__ void epi_chunk16(const EpiRegs& e, const uint32_t* raw, int cb, long long pix, uint4* out4, const float* grow) {
     float v[16];
-    const float* gp = grow ? grow + (cb % p.gate_c) : nullptr;
+    const float* gp = nullptr;   // gate row of this pixel's image, at this chunk's first channel (one modulo per 16 columns)
+    if constexpr (GATE) gp = grow ? grow + (cb % e.gate_c) : nullptr;
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
-        const float4 b = ld4(pb + cb + 4 * j4);
-        float x0 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 0]) + b.x, p.hs_slope, p.hs_offset);
-        float x1 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 1]) + b.y, p.hs_slope, p.hs_offset);
-        float x2 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 2]) + b.z, p.hs_slope, p.hs_offset);
-        float x3 = act_t<ACT>(__uint_as_float(raw[4 * j4 + 3]) + b.w, p.hs_slope, p.hs_offset);
+        const float4 b = ld_const4<PSM>(e.pb, e.pb_s, cb + 4 * j4);
+        float x0 = __uint_as_float(raw[4 * j4 + 0]) + b.x, x1 = __uint_as_float(raw[4 * j4 + 1]) + b.y;
+        float x2 = __uint_as_float(raw[4 * j4 + 2]) + b.z, x3 = __uint_as_float(raw[4 * j4 + 3]) + b.w;
+        if constexpr (ACT >= 0) {
+            x0 = act_t<ACT>(x0, e.hs_slope, e.hs_offset); x1 = act_t<ACT>(x1, e.hs_slope, e.hs_offset);
+            x2 = act_t<ACT>(x2, e.hs_slope, e.hs_offset); x3 = act_t<ACT>(x3, e.hs_slope, e.hs_offset);
+        } else {
+            x0 = tc_act(x0, e.act, e.hs_slope, e.hs_offset); x1 = tc_act(x1, e.act, e.hs_slope, e.hs_offset);
+            x2 = tc_act(x2, e.act, e.hs_slope, e.hs_offset); x3 = tc_act(x3, e.act, e.hs_slope, e.hs_offset);
+        }
         if constexpr (POST) {
-            const float4 sc = ld4(ps + cb + 4 * j4), sh = ld4(pt + cb + 4 * j4);
+            const float4 sc = ld_const4<PSM>(e.ps, e.ps_s, cb + 4 * j4), sh = ld_const4<PSM>(e.pt, e.pt_s, cb + 4 * j4);
             x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y); x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
         }
-        if (gp) {   // residual squeeze-excite: y + y * gate
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gp + 4 * j4));
-            x0 = fmaf(x0, g.x, x0); x1 = fmaf(x1, g.y, x1); x2 = fmaf(x2, g.z, x2); x3 = fmaf(x3, g.w, x3);
+        if constexpr (GATE) {
+            if (gp) {   // residual squeeze-excite: y + y * gate
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gp + 4 * j4));
+                x0 = fmaf(x0, g.x, x0); x1 = fmaf(x1, g.y, x1); x2 = fmaf(x2, g.z, x2); x3 = fmaf(x3, g.w, x3);
+            }
         }
         v[4 * j4 + 0] = x0; v[4 * j4 + 1] = x1; v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
     }
 #pragma unroll
     for (int h8 = 0; h8 < 2; h8++) {
-        if (p.res && pix >= 0 && cb + h8 * 8 < p.n_store) {
+        if (e.res && pix >= 0 && cb + h8 * 8 < e.n_store) {
             if constexpr (OUTF32) {
-                const float* rp = static_cast<const float*>(p.res) + size_t(pix) * p.res_cs + cb + h8 * 8;
+                const float* rp = static_cast<const float*>(e.res) + size_t(pix) * e.res_cs + cb + h8 * 8;
                 const float4 r0 = ld4(rp), r1 = ld4(rp + 4);
                 v[h8 * 8 + 0] += r0.x; v[h8 * 8 + 1] += r0.y; v[h8 * 8 + 2] += r0.z; v[h8 * 8 + 3] += r0.w;
                 v[h8 * 8 + 4] += r1.x; v[h8 * 8 + 5] += r1.y; v[h8 * 8 + 6] += r1.z; v[h8 * 8 + 7] += r1.w;
             } else {
-                const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + size_t(pix) * p.res_cs + cb + h8 * 8);
+                const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const __half*>(e.res) + size_t(pix) * e.res_cs + cb + h8 * 8);
                 const __half2* rh = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -318,9 +349,9 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* r
                 }
             }
         }
-        if (p.act2 != ACT_NONE) {
+        if (e.act2 != ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[h8 * 8 + j] = tc_act(v[h8 * 8 + j], p.act2, 0.f, 0.f);
+            for (int j = 0; j < 8; j++) v[h8 * 8 + j] = tc_act(v[h8 * 8 + j], e.act2, 0.f, 0.f);
         }
         if constexpr (OUTF32) {
             out4[2 * h8] = make_uint4(__float_as_uint(v[h8 * 8 + 0]), __float_as_uint(v[h8 * 8 + 1]), __float_as_uint(v[h8 * 8 + 2]),
@@ -339,10 +370,15 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* r
 // into a 128B-swizzled [128 pixels x 128 B] staging tile, the warps meet at a named barrier, and one thread hands the tile
 // to TMA (cp.async.bulk.tensor store): full-line, coalesced global writes, rows past the end of the tensor clipped by the
 // hardware.  A ring of kOutBufs staging tiles keeps kOutBufs - 1 stores in flight.
-template <int ACT, bool POST, bool OUTF32>
+template <int ACT, bool POST, bool OUTF32, bool PSM, bool GATE>
 __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* map_o, uint8_t* sout, uint32_t tmem_base,
                                            uint64_t* tmem_full, uint64_t* tmem_empty, const float* pb, const float* ps,
                                            const float* pt, int q, int half, int lane, bool issuer) {
+    EpiRegs e;
+    e.pb = pb; e.ps = ps; e.pt = pt;
+    e.pb_s = PSM ? smem_u32(pb) : 0u; e.ps_s = PSM ? smem_u32(ps) : 0u; e.pt_s = PSM ? smem_u32(pt) : 0u;
+    e.res = p.res; e.res_cs = p.res_cs; e.n_store = p.n_store; e.act = p.act; e.act2 = p.act2; e.gate_c = p.gate_c;
+    e.hs_slope = p.hs_slope; e.hs_offset = p.hs_offset;
     const int row = q * 32 + lane;
     const int total_tiles = p.num_m_tiles * p.n_chunks;
     constexpr int SUBC = OUTF32 ? 32 : 64;        // columns per 128-byte staging row
@@ -366,7 +402,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
             const long long m = (long long)m_tile * BLOCK_M + row;
             if (m < p.M) pix = m;
         }
-        const float* grow = (p.gate && pix >= 0) ? p.gate + size_t(pix / p.gate_rows) * p.gate_c : nullptr;
+        const float* grow = (GATE && p.gate && pix >= 0) ? p.gate + size_t(pix / p.gate_rows) * p.gate_c : nullptr;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
@@ -382,7 +418,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                     tmem_ld16_nowait(taddr + uint32_t(c0), raw0);       // .sync.aligned: whole (converged) warp
                     tmem_ld_wait();
                     uint4 o[4];
-                    epi_chunk16<ACT, POST, true>(p, raw0, pb, ps, pt, ch0 + c0, pix, o, grow);
+                    epi_chunk16<ACT, POST, true, PSM, GATE>(e, raw0, ch0 + c0, pix, o, grow);
 #pragma unroll
                     for (int j = 0; j < 4; j++) st_shared_16(buf + uint32_t(((j0 + j) ^ (row & 7)) << 4), o[j]);
                 } else {
@@ -392,11 +428,11 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                     if (two) tmem_ld16_nowait(taddr + uint32_t(c0 + 16), raw1);
                     tmem_ld_wait();
                     uint4 o[2];
-                    epi_chunk16<ACT, POST, false>(p, raw0, pb, ps, pt, ch0 + c0, pix, o, grow);
+                    epi_chunk16<ACT, POST, false, PSM, GATE>(e, raw0, ch0 + c0, pix, o, grow);
                     st_shared_16(buf + uint32_t(((j0 + 0) ^ (row & 7)) << 4), o[0]);
                     st_shared_16(buf + uint32_t(((j0 + 1) ^ (row & 7)) << 4), o[1]);
                     if (two) {
-                        epi_chunk16<ACT, POST, false>(p, raw1, pb, ps, pt, ch0 + c0 + 16, pix, o, grow);
+                        epi_chunk16<ACT, POST, false, PSM, GATE>(e, raw1, ch0 + c0 + 16, pix, o, grow);
                         st_shared_16(buf + uint32_t(((j0 + 2) ^ (row & 7)) << 4), o[0]);
                         st_shared_16(buf + uint32_t(((j0 + 3) ^ (row & 7)) << 4), o[1]);
                     }
@@ -421,14 +457,33 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
     if (issuer) tma_store_wait_all();
 }
 
+// Instantiations: the per-channel constants are in shared memory for every layer of up to kParamSmemMaxCh output channels
+// (compile-time activation, ld.shared constants); the fused squeeze-excite gate only exists on plain fp16 1x1 convolutions
+// (engine.cu: act none, no post-affine); wider layers (the CTC class projections) take the run-time-activation variant
+// that reads its constants from global memory.
 template <bool POST>
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUtensorMap* map_o, uint8_t* sout, uint32_t tmem_base,
                                                   uint64_t* tmem_full, uint64_t* tmem_empty, const float* pb, const float* ps,
                                                   const float* pt, int q, int half, int lane, bool issuer) {
-#define VSE_EPI(A)                                                                                                            \
-    do {                                                                                                                      \
-        if (p.tf32) epilogue_loop<A, POST, true>(p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer);  \
-        else epilogue_loop<A, POST, false>(p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer);       \
+#define VSE_EPI_ARGS p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer
+    if (!p.param_smem || (p.gate && (POST || p.tf32 || p.act != ACT_NONE))) {
+        if (p.gate) {   // not produced by the engine; kept correct rather than fast
+            if (p.tf32) epilogue_loop<-1, POST, true, false, true>(VSE_EPI_ARGS);
+            else epilogue_loop<-1, POST, false, false, true>(VSE_EPI_ARGS);
+        } else {
+            if (p.tf32) epilogue_loop<-1, POST, true, false, false>(VSE_EPI_ARGS);
+            else epilogue_loop<-1, POST, false, false, false>(VSE_EPI_ARGS);
+        }
+        return;
+    }
+    if (p.gate) {
+        if constexpr (!POST) epilogue_loop<ACT_NONE, false, false, true, true>(VSE_EPI_ARGS);
+        return;
+    }
+#define VSE_EPI(A)                                                                  \
+    do {                                                                            \
+        if (p.tf32) epilogue_loop<A, POST, true, true, false>(VSE_EPI_ARGS);        \
+        else epilogue_loop<A, POST, false, true, false>(VSE_EPI_ARGS);              \
     } while (0)
     switch (p.act) {
         case ACT_RELU: VSE_EPI(ACT_RELU); break;
@@ -440,6 +495,7 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUten
         default: VSE_EPI(ACT_NONE); break;
     }
 #undef VSE_EPI
+#undef VSE_EPI_ARGS
 }
 
 // ------------------------------------------------------------------------------------------------
