@@ -746,7 +746,7 @@ __device__ __forceinline__ void cta_fc(const float* in, int n_in, const float* _
     }
 }
 
-__global__ void __launch_bounds__(512) se_gate_kernel(SeDev p) {
+__global__ void __launch_bounds__(1024) se_gate_kernel(SeDev p) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
     extern __shared__ float sm[];
@@ -782,7 +782,7 @@ void launch_se_gate(const float* partial, int splits, int c_pad, int c, int cm, 
                     int cx, int cx_pad, int pre_ld) {
     SeDev d{partial, splits, c_pad, c, cm, tin, w1, b1, w2, b2, act1, act2, slope1, offset1, slope2, offset2, out,
             pre_w, pre_b, cx, cx_pad, pre_ld};
-    const int threads = 512;   // cm <= threads is checked by the caller
+    const int threads = 1024;   // cm <= 512 <= threads is checked by the caller; more threads = shorter dependent-load chains per FC
     pdl_launch(se_gate_kernel, n_img, threads, size_t(c + cm + threads + (pre_w ? cx : 0)) * sizeof(float), st, d);
 }
 
