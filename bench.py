@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     fps = args.steps * per_step / dt
     sample = f"{per_step} of the {args.batch} frames of each step ({args.height}x{args.width}), one frame per call, rec batches <= 6"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -403,13 +403,37 @@ def run_b200(args, rank, local_rank, world):
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        emit(out)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries the one JSON line and nothing else: libraries that print to file descriptor 1 (NCCL's version banner
+    does, whatever NCCL_DEBUG_FILE says) are sent to stderr, and emit() writes the result to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
     args = parse_args()
     apply_model_args(args)
     rank, local_rank, world = env_rank()
+    if not (args.impl != "reference" and world == 1 and args.gpus > 1):   # the torchrun re-launch keeps the child's stdout
+        claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
