@@ -195,8 +195,8 @@ static void frame_strides(const uint8_t* const* frames, const int32_t* h, const 
 }
 
 // host frames -> one staging buffer, 256-byte aligned slots, async on `st`
-static void stage_frames(const uint8_t* const* frames, const int32_t* h, const std::vector<int>& fstride, int n, DevBuf& buf,
-                         cudaStream_t st, std::vector<const uint8_t*>& fdev) {
+static void stage_frames(const uint8_t* const* frames, const int32_t* h, const int32_t* w, const std::vector<int>& fstride, int n,
+                         DevBuf& buf, cudaStream_t st, std::vector<const uint8_t*>& fdev) {
     size_t total = 0;
     for (int i = 0; i < n; i++) total += (size_t(h[i]) * fstride[i] + 255) & ~size_t(255);
     buf.reserve(total);
@@ -209,7 +209,9 @@ static void stage_frames(const uint8_t* const* frames, const int32_t* h, const s
         run_bytes = 0;
     };
     for (int i = 0; i < n; i++) {
-        const size_t bytes = size_t(h[i]) * fstride[i];
+        // a strided view (sub-area of a larger frame) ends with its last pixel, not with a full row pitch: reading
+        // h * stride bytes would run past the end of the caller's frame for an area that touches its bottom edge
+        const size_t bytes = size_t(h[i] - 1) * fstride[i] + size_t(w[i]) * 3;
         if (run_bytes && frames[i] == run_src + run_bytes && off == run_off + run_bytes) {
             run_bytes += bytes;
         } else {
@@ -242,7 +244,7 @@ void Engine::prefetch_frames(const uint8_t* const* frames, const int32_t* h, con
     pe.buf = P->pending.empty() ? 0 : 1 - P->pending[0].buf;
     pe.dev.assign(n, nullptr);
     // growing the buffer frees the old allocation (implicit device sync); the run that last used it has returned
-    stage_frames(frames, h, fstride, n, P->fbuf[pe.buf], P->copy_stream, pe.dev);
+    stage_frames(frames, h, w, fstride, n, P->fbuf[pe.buf], P->copy_stream, pe.dev);
     VSE_CUDA(cudaEventRecord(P->fdone[pe.buf], P->copy_stream));
     pe.src.assign(frames, frames + n);
     pe.h.assign(h, h + n);
@@ -292,7 +294,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
             } else if (P->pending.size() == 1) {
                 buf = 1 - P->pending[0].buf;
             }
-            stage_frames(frames, h, fstride, n, P->fbuf[buf], stream, fdev);
+            stage_frames(frames, h, w, fstride, n, P->fbuf[buf], stream, fdev);
         }
     }
     VSE_CUDA(cudaEventRecord(P->ev[1], stream));
