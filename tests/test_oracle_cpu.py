@@ -113,3 +113,33 @@ def test_all_shipped_models_compile():
             assert plan.steps and plan.output_vids
             n += 1
     assert n == 21
+
+
+@needs_ref
+def test_rnn_oracle_matches_torch_lstm():
+    """Paddle's `rnn` op (V2/ch_rec op#140: 2-layer bidirectional LSTM, gate order i,f,g,o, WeightList = all weights then all
+    biases) as restated in oracle/graph_interp.py::_rnn, against torch.nn.LSTM loaded with the same shipped weights — an
+    independent implementation of the same recurrence."""
+    from oracle.graph_interp import GraphInterpreter
+    from video_subtitle_extractor_b200.loader import load_model
+    model = load_model(f"{REF}/backend/models/V2/ch_rec")
+    gi = GraphInterpreter(model)
+    op = [o for o in model.program.ops if o.type == "rnn"][0]
+    a = op.attrs
+    assert (a["mode"], a["hidden_size"], a["num_layers"], a["is_bidirec"]) == ("LSTM", 256, 2, True)
+    wl = [gi._get({}, n) for n in op.inputs["WeightList"]]
+    lstm = torch.nn.LSTM(a["input_size"], a["hidden_size"], a["num_layers"], bidirectional=True)
+    nw = 4
+    with torch.no_grad():
+        for layer in range(2):
+            for d, suffix in enumerate(("", "_reverse")):
+                k = layer * 2 + d
+                getattr(lstm, f"weight_ih_l{layer}{suffix}").copy_(wl[2 * k])
+                getattr(lstm, f"weight_hh_l{layer}{suffix}").copy_(wl[2 * k + 1])
+                getattr(lstm, f"bias_ih_l{layer}{suffix}").copy_(wl[2 * nw + 2 * k])
+                getattr(lstm, f"bias_hh_l{layer}{suffix}").copy_(wl[2 * nw + 2 * k + 1])
+        x = torch.from_numpy(np.random.default_rng(3).standard_normal((37, 3, a["input_size"])).astype(np.float32))
+        want, _ = lstm(x)
+        got = gi._rnn(op, {op.inp("Input"): x})
+    assert got.shape == want.shape == (37, 3, 512)
+    assert float((got - want).abs().max()) < 1e-5
