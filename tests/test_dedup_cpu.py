@@ -29,3 +29,19 @@ def test_concat_and_dedup_match_reference_methods():
         assert [list(u) for u in got] == c["unique"]
         subtitles += len(got)
     assert merged > 30 and subtitles > 100
+
+
+def test_srt_writer_matches_reference_generate_subtitle_file():
+    with open(os.path.join(os.path.dirname(GOLDEN), "srt_golden.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    table = g["pos_msec_after_seek_and_read"]
+    n = 0
+    for c in g["cases"]:
+        subs = dedup.remove_duplicates(c["lines"], 0.8, use_vsf=False)
+        text, short = dedup.srt_text(subs, g["fps"], lambda frame_no: table[str(frame_no)])
+        assert text == c["srt"]
+        assert short == c["short_lines"]
+        n += len(subs)
+    assert n > 25 and any(v is None for v in table.values())      # the decoder-failure fallback is exercised too
+    assert dedup.timecode_from_msec(3723004.9) == "01:02:03,004"
+    assert dedup.timecode_from_frame(4597, 29.97002997002997) == "00:02:33,011"

@@ -80,3 +80,47 @@ def remove_duplicates(lines: Sequence[str], threshold: float = 0.8, use_vsf: boo
         out.append((start, end, run[best][1]))
         i = j + 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# SRT writer — `SubtitleExtractor.generate_subtitle_file` / `_frame_to_timecode`, reference backend/main.py:614-636, 731-766
+# (the VideoSubFinder variant of the writer is out of scope with VideoSubFinder itself).  Pinned by
+# tests/golden/srt_golden.json: the reference's own methods on its sample video test/test_en.mp4.
+# ------------------------------------------------------------------------------------------------------------------------
+def timecode_from_frame(frame_no: int, fps: float) -> str:
+    """Fallback of the reference when the decoder cannot deliver the frame: HH:MM:SS from the frame count and, as the last
+    field, the frame's index inside its second (`frame_no % fps`) — not milliseconds; kept as the reference writes it."""
+    return "{0:02d}:{1:02d}:{2:02d},{3:03d}".format(int(frame_no / (3600 * fps)), int(frame_no / (60 * fps) % 60),
+                                                    int(frame_no / fps % 60), int(frame_no % fps))
+
+
+def timecode_from_msec(msec: float) -> str:
+    """HH:MM:SS,mmm from the decoder's position in milliseconds (truncated, as the reference does)."""
+    seconds, ms = msec // 1000, int(msec % 1000)
+    minutes = hours = 0
+    if seconds >= 60:
+        minutes, seconds = int(seconds // 60), int(seconds % 60)
+    if minutes >= 60:
+        hours, minutes = int(minutes // 60), int(minutes % 60)
+    return "%02d:%02d:%02d,%03d" % (hours, minutes, seconds, ms)
+
+
+def srt_text(subtitles: Sequence[Tuple[str, str, str]], fps: float, pos_msec=None) -> Tuple[str, List[int]]:
+    """-> (contents of the .srt file, 1-based numbers of the subtitles that were stretched to one second).
+
+    `subtitles`: output of `remove_duplicates`.  `pos_msec(frame_no)` returns the decoder's timestamp of that frame in
+    milliseconds (what cv2 reports as CAP_PROP_POS_MSEC after seeking to the frame and reading it) or None when the frame
+    cannot be read; without it, or for a timestamp <= 0, the frame-count fallback is used.  A subtitle shorter than one
+    second of frames ends one second (`int(start + fps)` frames) after its start."""
+    def timecode(frame_no: int) -> str:
+        ms = pos_msec(frame_no) if pos_msec is not None else None
+        return timecode_from_frame(frame_no, fps) if ms is None or ms <= 0 else timecode_from_msec(ms)
+
+    out, stretched = [], []
+    for number, (start, end, text) in enumerate(subtitles, 1):
+        first, last = int(start), int(end)
+        if abs(last - first) < fps:
+            last = int(first + fps)
+            stretched.append(number)
+        out.append(f"{number}\n{timecode(first)} --> {timecode(last)}\n{text}\n")
+    return "".join(out), stretched
