@@ -106,7 +106,10 @@ const char* vse_last_error(const vse_engine* e);
 int  vse_load_plan(vse_engine* e, int32_t which, const void* blob, size_t nbytes);
 
 /* det + rec on n_frames BGR uint8 HWC frames (row_stride in bytes, may be NULL for tight rows).
- * TextSystem order: boxes sorted top-to-bottom / left-to-right per frame. */
+ * TextSystem order: boxes sorted top-to-bottom / left-to-right per frame.
+ * A frame may be a VIEW of a larger image (the reference's half-frame / subtitle-area crop, frame_preprocess,
+ * backend/tools/subtitle_ocr.py:270-289): pass the address of the view's first pixel, the view's h / w and the full image's
+ * row pitch; the engine reads (h - 1) * row_stride + 3 * w bytes from there and returns boxes in the view's coordinates. */
 int  vse_run(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const int32_t* w,
              const int32_t* row_stride, int32_t n_frames, int32_t mem_kind, vse_result* out);
 
