@@ -1,8 +1,15 @@
 """BASELINE configs[0] as plumbing on the CPU: a stretch of the reference's test/test_en.mp4 in fast mode with the default
 subtitle area -> frame schedule (frames.py) -> predictor (here the CPU oracle; on a B200 box the engine) -> reading order,
 ROI filter and raw.txt lines (rawtxt.py) -> de-dup and .srt text (dedup.py).  Checks that the host modules either side of
-the predictor call fit together and produce the subtitle the video shows (SURVEY.md Appendix E anchor)."""
+the predictor call fit together and produce the subtitle the video shows (SURVEY.md Appendix E anchor), and that the
+REFERENCE'S OWN glue — OcrRecogniser.predict, extract_subtitles, _remove_duplicate_subtitle, generate_subtitle_file, run
+unmodified in a separate process (tests/golden/ref_glue_runner.py) on the same predictor outputs and the same video —
+writes the identical raw.txt lines and the identical .srt text."""
+import json
 import os
+import subprocess
+import sys
+import tempfile
 
 import cv2
 import pytest
@@ -24,13 +31,14 @@ def test_fast_mode_stretch_of_test_en_to_srt():
     area = (int(w * 0.05), int(w * 0.95), int(h * 0.78), int(h * 0.99))
     schedule = [k for k in frames.fast_mode_frames(n_frames, fps, 3) if 270 <= k <= 345]
     assert schedule == list(range(271, 346, 9))
-    lines = []
+    lines, per_frame = [], []
     for k in schedule:
         cap.set(cv2.CAP_PROP_POS_FRAMES, k - 1)          # what ocr_task_producer does (subtitle_ocr.py:191)
         ok, frame = cap.read()
         assert ok
         r = orc.ocr(frame)
         rec = [(hl.ids_to_text(ids, hl.EN_CHARACTERS), float(s)) for ids, s in zip(r.ids, r.scores)]
+        per_frame.append(dict(no=k, quads=[[[float(x), float(y)] for x, y in b] for b in r.boxes], rec=[[t, p] for t, p in rec]))
         dt_box, res = rawtxt.order_like_predict([b for b in r.boxes], rec)
         lines += rawtxt.frame_lines(k, dt_box, res, sub_area=area, rec_char_type="en", drop_score=0.75)
     assert len(lines) >= 5 and all(l.split("\t")[0].isdigit() for l in lines)
@@ -50,3 +58,18 @@ def test_fast_mode_stretch_of_test_en_to_srt():
     start, end = blocks[1].split("\n")[1].split(" --> ")
     assert "00:00:09,000" <= start < end <= "00:00:12,000"    # frames ~280..340 of a 29.97 fps video
     assert "Yami" not in text                              # the title at the top of the frame is outside the subtitle area
+
+    # the same predictor outputs through the REFERENCE'S OWN glue, untouched, in its own process: identical raw.txt and .srt
+    with tempfile.TemporaryDirectory() as tmp:
+        job = dict(video=VIDEO, fps=fps, area=dict(xmin=area[0], xmax=area[1], ymin=area[2], ymax=area[3]), frames=per_frame,
+                   options=dict(REC_CHAR_TYPE="en", DROP_SCORE=0.75, SUB_AREA_DEVIATION_RATE=0.0, DEBUG_OCR_LOSS=False))
+        with open(os.path.join(tmp, "in.json"), "w", encoding="utf-8") as f:
+            json.dump(job, f, ensure_ascii=False)
+        runner = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_glue_runner.py")
+        p = subprocess.run([sys.executable, runner, os.path.join(tmp, "in.json"), os.path.join(tmp, "out.json")],
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-600:]
+        with open(os.path.join(tmp, "out.json"), encoding="utf-8") as f:
+            ref = json.load(f)
+    assert ref["raw_lines"] == lines
+    assert ref["srt"] == text
