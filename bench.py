@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--det", default=None, help="detector model (default V4/ch_det_fast = BASELINE configs[1]); needs its packed plan")
     ap.add_argument("--rec", default=None, help="recogniser model (default V4/en_rec_fast)")
     ap.add_argument("--flags", type=int, default=0, help="vse_config.flags (VSE_FLAG_* A/B switches, profiling only)")
+    ap.add_argument("--precision", default=None, choices=["fp16", "fp32", "tf32", "fp32_tc"],
+                    help="activation / product precision (default: engine.bench_mode(), the mode held to the parity bar)")
+    ap.add_argument("--frame-stride", type=int, default=7, help="synthetic stream index step between consecutive frames of the pool")
     return ap.parse_args()
 
 
@@ -59,6 +62,22 @@ def apply_model_args(args):
         DET = args.det
     if args.rec:
         REC = args.rec
+
+
+def frame_index(p: int, k: int, world_b: int, stride: int) -> int:
+    """Index into the synthetic stream of frame k of global batch p: consecutive frames are `stride` stream frames apart, so a
+    pool of 3 x 32 frames walks over ~11 subtitles (45 frames of text + 15 blank each), not 2."""
+    return (p * world_b + k) * stride
+
+
+def workload_config(args, world: int):
+    """The `config` object both arms print (the driver compares them)."""
+    B, H, W = args.batch, args.height, args.width
+    return {"workload": f"synthetic {H}p subtitle frames (SURVEY.md §8d generator), {DET} + {REC}",
+            "frames_per_step_per_gpu": B, "global_frames_per_step": world * B, "frame": [H, W, 3],
+            "parallelism": f"frame-range sharding x{world}",
+            "frames": f"stream index (pool_batch * {world * B} + k) * {args.frame_stride}, {args.pool} pool batches cycled",
+            "l2": f"inputs larger than L2: {args.pool} distinct batches x {B * H * W * 3 / 1e6:.0f} MB cycled"}
 
 
 def env_rank():
@@ -143,24 +162,26 @@ def run_reference(args, rank, world):
     oracle, cores = cpu_oracle(det_blob, rec_blob)
     per_step = 4                                     # bounded sample of the 32-frame batch per step
     stream = SynthStream(args.height, args.width)
-    frames = [stream.frame(i * 7) for i in range(per_step * 2)]
+    # the SAME frames the B200 arm times: frames 0, 8, 16, 24 of pool batch (step mod pool) of rank 0
+    B = args.batch
+    pick = [k * (B // per_step) for k in range(per_step)]
+    frames = {(p, k): stream.frame(frame_index(p, k, world * B, args.frame_stride)) for p in range(args.pool) for k in pick}
     for _ in range(max(args.warmup, 1)):
-        oracle.ocr(frames[0])
+        oracle.ocr(frames[(0, 0)])
     t0 = time.perf_counter()
     for s in range(args.steps):
-        for k in range(per_step):
-            oracle.ocr(frames[(s * per_step + k) % len(frames)])
+        for k in pick:
+            oracle.ocr(frames[(s % args.pool, k)])
     dt = time.perf_counter() - t0
     fps = args.steps * per_step / dt
-    sample = f"{per_step} of the {args.batch} frames of each step ({args.height}x{args.width}), one frame per call, rec batches <= 6"
+    sample = (f"frames {pick} of the {B} frames of each step's batch ({args.height}x{args.width}), one frame per call, rec batches <= 6")
     emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {args.height}p subtitle frames (SURVEY.md §8d generator), {DET} + {REC}",
-                   "frames_per_step_per_gpu": args.batch, "frame": [args.height, args.width, 3],
-                   "arm": "CPU restatement of the reference path (torch-CPU fp32 + cv2, all host threads), bounded sample: "
-                          f"{per_step} of the {args.batch} frames of each step"},
+        "config": workload_config(args, world),
+        "arm": "CPU restatement of the reference path (torch-CPU fp32 + cv2, all host threads), bounded sample: "
+               f"{per_step} of the {args.batch} frames of each step",
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,8 +215,8 @@ def step_roofline(eng, E):
                 continue
             pad8 = lambda c: (c + 7) // 8 * 8
             wbytes = taps * cin * cout * 4 if op in (P.OP_CONV, P.OP_STEM, P.OP_DECONV2) else taps * cin * 4
-            if kind == 1:
-                wbytes //= 2       # fp16 weight matrix
+            if kind == 1 and eb_in == 2:
+                wbytes //= 2       # fp16 weight matrix (fp32 activations: tf32 words or fp16 hi + lo, 4 bytes per weight)
             out_bytes = pout * (cout if eb_out == 4 else pad8(cout)) * eb_out
             if op == P.OP_STEM:
                 bytes_ = pin * 4 + pout * pad8(cout) * eb_out + wbytes
@@ -287,7 +308,7 @@ def run_b200(args, rank, local_rank, world):
     host_batches, dev_batches = [], []
     for p in range(args.pool):
         lo, hi = shard.frame_range(rank, world, world * B)
-        idx = [p * world * B + k for k in range(lo, hi)]
+        idx = [frame_index(p, k, world * B, args.frame_stride) for k in range(lo, hi)]
         pinned = torch.empty((len(idx), H, W, 3), dtype=torch.uint8, pin_memory=True)
         arr = pinned.numpy()
         for j, i in enumerate(idx):
@@ -298,7 +319,17 @@ def run_b200(args, rank, local_rank, world):
 
     # V2 recognisers (ResNet + BiLSTM) read 32-pixel-high crops (reference backend/tools/paddle_model_config.py:94-97)
     rec_h = 32 if REC.startswith("V2/") else 48
-    eng = E.Engine(device=local_rank, precision=E.PRECISION_FP16, flags=args.flags, rec_image_h=rec_h)
+    mode = dict(E.bench_mode())
+    if args.precision:
+        mode["precision"] = {"fp16": E.PRECISION_FP16, "fp32": E.PRECISION_FP32, "tf32": E.PRECISION_TF32,
+                             "fp32_tc": E.PRECISION_FP32_TC}[args.precision]
+    mode["flags"] = mode.get("flags", 0) | args.flags
+    prec_name = {E.PRECISION_FP16: "fp16 activations, fp32 accumulate (NOT the parity mode: DESIGN.md §5)",
+                 E.PRECISION_FP32: "fp32 activations, CUDA-core kernels",
+                 E.PRECISION_TF32: "fp32 activations, tf32 tensor-core products",
+                 E.PRECISION_FP32_TC: "fp32 activations; tensor-core products on fp16 hi+lo splits of both operands "
+                                      "(3 MMAs per product), fp32 accumulate"}[mode["precision"]]
+    eng = E.Engine(device=local_rank, rec_image_h=rec_h, **mode)
     eng.load_plan(E.PLAN_DET, det_blob, DET)
     eng.load_plan(E.PLAN_REC, rec_blob, REC)
     hs, ws = [H] * B, [W] * B
@@ -330,6 +361,7 @@ def run_b200(args, rank, local_rank, world):
         l0 = eng.launch_count
         t0 = time.perf_counter()
         n_lines = 0
+        widths = []
         if pf:
             prefetch(batches, 0)
         for k in range(args.steps):
@@ -338,14 +370,19 @@ def run_b200(args, rank, local_rank, world):
             res = step(batches, k, mem_kind)
             dev_ms += float(eng.last_timings[7])
             n_lines += sum(len(r.quads) for r in res)
+            widths += [int(w_) for r in res for w_ in r.rec_widths]
         barrier()
         wall = time.perf_counter() - t0
+        timed.mean_width = float(np.mean(widths)) if widths else 0.0
         return wall, dev_ms / 1e3, eng.launch_count - l0, n_lines, res
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # clocks are sampled on rank 0 only (one nvidia-smi child per box, not one per rank, inside the timed region)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     wall, dev_s, launches, n_lines, last = timed(dev_batches, E.MEM_DEVICE)
-    clocks = sampler.stop()
+    mean_width = timed.mean_width
+    clocks = sampler.stop() if sampler else None
     wall_e2e, dev_s_e2e, _, _, last_e2e = timed(host_batches, E.MEM_PINNED)
     stage_ms = [float(x) for x in eng.last_timings]
     # one extra un-prefetched call: its stage 0 is the bare host->device copy time of one batch on this box (PCIe rate)
@@ -354,6 +391,11 @@ def run_b200(args, rank, local_rank, world):
 
     wall_max = shard.max_over_ranks(wall, dev)
     wall_e2e_max = shard.max_over_ranks(wall_e2e, dev)
+    per_rank = [(rank, wall / args.steps * 1e3, dev_s / args.steps * 1e3, wall_e2e / args.steps * 1e3, n_lines / max(args.steps, 1))]
+    if world > 1:
+        bucket = [None] * world
+        torch.distributed.all_gather_object(bucket, per_rank[0])
+        per_rank = bucket
     total_frames = world * B * args.steps
     value = total_frames / wall_max
     e2e_value = total_frames / wall_e2e_max
@@ -387,12 +429,12 @@ def run_b200(args, rank, local_rank, world):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"synthetic {H}p subtitle frames (SURVEY.md §8d generator), {DET} + {REC}",
-                       "frames_per_step_per_gpu": B, "global_frames_per_step": world * B, "frame": [H, W, 3],
-                       "parallelism": f"frame-range sharding x{world}", "text_lines_per_step": n_lines / max(args.steps, 1),
-                       "l2": f"inputs larger than L2: {args.pool} distinct batches x {B * frame_bytes / 1e6:.0f} MB cycled",
-                       "precision": "fp16 activations, fp32 accumulate" + (f"; vse_config.flags={args.flags}" if args.flags else "")},
+            "dtype": "f16" if mode["precision"] == E.PRECISION_FP16 else "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "precision": prec_name + (f"; vse_config.flags={args.flags}" if args.flags else ""),
+            "text_lines_per_frame": n_lines / max(args.steps * B, 1), "mean_padded_rec_width": mean_width,
+            "per_rank": [{"rank": r, "ms_per_step": round(a, 4), "device_ms_per_step": round(b, 4), "e2e_ms_per_step": round(c, 4),
+                          "text_lines_per_step": d} for r, a, b, c, d in per_rank],
             "device_ms_per_step": dev_s / args.steps * 1e3, "stage_ms_last_e2e_step": stage_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_max / args.steps * 1e3, "device_ms_per_step": dev_s_e2e / args.steps * 1e3,

@@ -47,7 +47,11 @@ enum { VSE_PLAN_DET = 0, VSE_PLAN_REC = 1 };
 enum {
     VSE_PRECISION_FP16 = 0, /* fp16 activations, fp32 accumulate: tcgen05 kind::f16 convolutions + specialised kernels   */
     VSE_PRECISION_FP32 = 1, /* fp32 activations, CUDA-core kernels only: the exact-parity mode                             */
-    VSE_PRECISION_TF32 = 2  /* fp32 activations (full range), convolutions on tcgen05 kind::tf32 (10-bit mantissa operands) */
+    VSE_PRECISION_TF32 = 2, /* fp32 activations (full range), convolutions on tcgen05 kind::tf32 (10-bit mantissa operands) */
+    VSE_PRECISION_FP32_TC = 3 /* fp32 activations; convolutions on tcgen05 kind::f16 with both operands split into fp16 hi + lo
+                               * (three MMAs per product, ~22-bit operands): the fp32 engine's results at tensor-core speed —
+                               * the mode that meets the parity bar on real video and the one bench.py times.  Needs activations
+                               * inside the fp16 range (like VSE_PRECISION_FP16; violations are reported, never silent) */
 };
 enum {
     VSE_FLAG_NO_TENSOR_CORES = 1, /* vse_config.flags: keep every conv on the CUDA-core kernels (A/B checks)      */
@@ -104,6 +108,13 @@ const char* vse_last_error(const vse_engine* e);
 /* Packed plan (steps + fp32 weights) produced by video_subtitle_extractor_b200/plan.py from the
  * reference's inference.pdmodel/.pdiparams; on multi-GPU jobs rank 0 builds it and broadcasts the bytes. */
 int  vse_load_plan(vse_engine* e, int32_t which, const void* blob, size_t nbytes);
+
+/* Optional, VSE_PRECISION_FP32_TC only: absmax[k] = the largest |activation| the INPUT of plan step k is expected to hold
+ * (calibrated offline: tools/calibrate_ranges.py -> video_subtitle_extractor_b200/calibration/<model>.json; <= 0 = unknown).
+ * The engine scales each convolution's operand rows by the power of two that brings absmax[k] just below 2^14 before the
+ * fp16 hi/lo split (4x headroom to the fp16 limit; an input that still overflows is reported as non-finite output, never
+ * silently).  Without the call every convolution uses a conservative 2^2.  Must follow vse_load_plan of that plan. */
+int  vse_set_conv_input_ranges(vse_engine* e, int32_t which, const float* absmax, int32_t n_steps);
 
 /* det + rec on n_frames BGR uint8 HWC frames (row_stride in bytes, may be NULL for tight rows).
  * TextSystem order: boxes sorted top-to-bottom / left-to-right per frame.

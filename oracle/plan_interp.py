@@ -70,9 +70,11 @@ class PlanInterpreter:
         return _act(y, s.p.get("act2", P.ACT_NONE))
 
     @torch.no_grad()
-    def run(self, x: torch.Tensor, valid_w: Optional[List[int]] = None, keep_all: bool = False):
+    def run(self, x: torch.Tensor, valid_w: Optional[List[int]] = None, keep_all: bool = False, store_hook=None):
         """x: normalised float NCHW, or uint8 NHWC (normalised here with the plan's constants;
-        columns >= valid_w[n] are zero in normalised space, as the reference's right zero-pad)."""
+        columns >= valid_w[n] are zero in normalised space, as the reference's right zero-pad).
+        store_hook(step_index, step, tensor) -> tensor, if given, is applied to every step output before it is stored
+        (tools/precision_study.py emulates the engine's 16-bit activation storage with it)."""
         plan = self.plan
         if x.dtype == torch.uint8:
             sc = torch.tensor(plan.norm_scale).reshape(1, 1, 1, 3)
@@ -87,6 +89,8 @@ class PlanInterpreter:
         vals = plan.values
 
         def put(vid: int, t: torch.Tensor):
+            if store_hook is not None:
+                t = store_hook(step_no[0], cur[0], t)
             env[vid] = t
             v = vals[vid]
             if v.alias_of >= 0:
@@ -98,7 +102,9 @@ class PlanInterpreter:
             parts = sorted(views[vid], key=lambda p: p[0])
             env[vid] = torch.cat([t for _, t in parts], dim=1)
 
-        for s in plan.steps:
+        step_no, cur = [0], [None]
+        for k, s in enumerate(plan.steps):
+            step_no[0], cur[0] = k, s
             for v in s.ins:
                 materialise(v)
             op = s.op

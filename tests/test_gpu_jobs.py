@@ -1,0 +1,128 @@
+"""Whole-video jobs through the CUDA engine (BASELINE configs[0], [2], [3]): frame feed -> vse_run ->
+raw.txt lines -> de-dup -> .srt, compared with what the REFERENCE'S OWN glue writes from the graph-level oracle's predictor
+outputs for the same videos (tests/golden/make_job_golden.py, make_accurate_video_golden.py: OcrRecogniser.predict,
+extract_subtitles, extract_frame_by_det, _remove_duplicate_subtitle, generate_subtitle_file run untouched).
+
+Needs tests/golden/_videos/ (copies made by __graft_entry__.build()) and the packed plans; both travel with the snapshot.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from video_subtitle_extractor_b200 import charset, frames as F, job, weights
+from video_subtitle_extractor_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+VIDEOS = os.path.join(GOLDEN, "_videos")
+OUT = os.path.join(os.path.dirname(HERE), "gpurun_out")
+
+
+def _engine(det, rec, **kw):
+    for m in (det, rec):
+        if not weights.have_plan(m):
+            pytest.skip(f"packed plan for {m} not present on this machine")
+    eng = E.Engine(**(kw or E.bench_mode()))
+    eng.load_plan(E.PLAN_DET, weights.load_plan_blob(det), det)
+    eng.load_plan(E.PLAN_REC, weights.load_plan_blob(rec), rec)
+    return eng
+
+
+def _video(name):
+    path = os.path.join(VIDEOS, name)
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/_videos/ is absent (run __graft_entry__.build() where the reference tree exists)")
+    return path
+
+
+def _fields(line):
+    no, coord, text = line.rstrip("\n").split("\t")
+    return int(no), tuple(int(v) for v in coord.strip("()").split(",")), text
+
+
+@pytest.mark.parametrize("video,det,rec,lang,n_classes", [("test_en", "V4/ch_det_fast", "V4/en_rec_fast", "en", 97),
+                                                          ("test_cn", "V4/ch_det_fast", "V4/ch_rec_fast", "ch", 6625)])
+def test_fast_mode_job_writes_the_reference_glue_output(video, det, rec, lang, n_classes):
+    """BASELINE configs[0] with the engine as predictor (and one video of configs[3]): fast mode, default subtitle area."""
+    with open(os.path.join(GOLDEN, f"job_golden_{video}.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    with open(os.path.join(GOLDEN, f"video_golden_{video}.json")) as f:
+        vg = json.load(f)
+    sched = [fr["no"] for fr in vg["frames"]]
+    assert sched == F.fast_mode_frames(vg["frame_count"], vg["fps"])
+    path = _video(g["video"])
+    eng = _engine(det, rec)
+    res = job.fast_mode_job(eng, path, charset.characters(lang, None, n_classes), sub_area=tuple(g["area"]), rec_char_type=lang,
+                            drop_score=g["drop_score"])
+    eng.close()
+    # f1: the feed delivers exactly the frames `extract_frame_by_fps` turns into OCR tasks (the golden run's schedule)
+    assert res.frame_numbers == sched
+    # f3: raw.txt lines — same frames, same texts; rectangles identical (a rectangle may move by a pixel where the engine's
+    # box differs from the oracle's inside the IoU >= 0.99 bar)
+    got, want = [_fields(l) for l in res.lines], [_fields(l) for l in g["raw_lines"]]
+    assert [(a[0], a[2]) for a in got] == [(b[0], b[2]) for b in want]
+    moved = [(a, b) for a, b in zip(got, want) if a[1] != b[1]]
+    assert all(max(abs(x - y) for x, y in zip(a[1], b[1])) <= 2 for a, b in moved), moved[:3]
+    assert len(moved) <= 0.02 * len(want), (len(moved), len(want))
+    # de-dup + SRT writer: the reference's own .srt, byte for byte
+    assert res.srt == g["srt"]
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"job_{video}.srt"), "w", encoding="utf-8") as f:
+        f.write(res.srt)
+
+
+def test_accurate_mode_job_matches_the_reference_loop():
+    """BASELINE configs[2]: test_cn.mp4, accurate mode, V4/ch_det + V4/ch_rec, 64 frames per vse_run — on the stretch of the
+    video the graph-level oracle was run on (the server graphs cost ~12 s per frame on the CPU)."""
+    with open(os.path.join(GOLDEN, "accurate_video_golden_test_cn.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    path = _video(g["video"])
+    eng = _engine(*g["models"], **E.accurate_mode())
+    res = job.accurate_mode_job(eng, path, charset.characters("ch", None, 6625), batch=64, sub_area=tuple(g["area"]),
+                                rec_char_type="ch", first=g["first"], last=g["last"])
+    eng.close()
+    # per-frame predictor parity on every frame of the stretch: boxes IoU >= 0.99 / ids equal
+    from tests.test_gpu_real_video import edit_distance, iou_quads
+    n_box = bad = sym = err = 0
+    for fr in g["frames"]:
+        r = res.results[fr["no"]]
+        assert len(r.quads) == len(fr["boxes"]), (fr["no"], len(r.quads), len(fr["boxes"]))
+        for q, b, ids, gids in zip(r.quads, fr["boxes"], r.ids, fr["ids"]):
+            n_box += 1
+            if q.astype(int).tolist() != b and iou_quads(q, b, fr["shape"][:2]) < 0.99:
+                bad += 1
+            err += edit_distance(ids, gids)
+            sym += len(gids)
+    print(f"\naccurate stretch: {len(g['frames'])} frames, {n_box} boxes, IoU<0.99: {bad}, CER {err / max(sym, 1):.2e}")
+    assert n_box >= 150 and bad == 0 and err / max(sym, 1) <= 1e-3
+    # f2: the queued tasks of the reference's own extract_frame_by_det (frame numbers relative to the stretch; cached or not)
+    assert [(t[0], t[1] is not None) for t in res.tasks] == [(t["frame_no"], t["cached"]) for t in g["tasks"]]
+    # f3: raw.txt lines and .srt of the reference's own worker / writer
+    assert res.lines == g["raw_lines"]
+    assert res.srt == g["srt"]
+
+
+def test_frame_feed_half_frame_views_and_ranges():
+    """f1: the feed's half-frame crop is the reference's `frame_preprocess` slice (zero-copy view) and a rank's frame range
+    starts where the previous one ends — results equal the ones of contiguous copies of the same rows."""
+    path = _video("test_en.mp4")
+    eng = _engine("V4/ch_det_fast", "V4/en_rec_fast")
+    feed = job.FrameFeed(path, 271, 335, list(range(271, 336, 8)), batch=4, half="lower")
+    got = job.run_feed(eng, feed)
+    import cv2
+    cap = cv2.VideoCapture(path)
+    cap.set(cv2.CAP_PROP_POS_FRAMES, 270)
+    no = 270
+    n_lines = 0
+    while no < 335:
+        ok, frame = cap.read()
+        no += 1
+        if no in got:
+            want = eng.run([np.ascontiguousarray(frame[frame.shape[0] // 2:])])[0]
+            assert np.array_equal(got[no].quads, want.quads) and got[no].ids == want.ids
+            n_lines += len(want.quads)
+    eng.close()
+    assert sorted(got) == list(range(271, 336, 8)) and n_lines >= 5

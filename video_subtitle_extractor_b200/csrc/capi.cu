@@ -14,6 +14,9 @@ static thread_local std::string g_create_error;
 template <typename F>
 static int guarded(vse_engine* e, F&& f) {
     try {
+        // the engine's streams, buffers and kernels belong to its device: every entry point selects it, so calls from another
+        // thread (or after an engine on another GPU was created in this thread) do not run against the wrong current device
+        if (e && cudaSetDevice(e->impl->cfg.device) != cudaSuccess) throw vse::CudaError{"cudaSetDevice failed"};
         f();
         return VSE_OK;
     } catch (const vse::CudaError& ce) {
@@ -86,6 +89,7 @@ int vse_create(const vse_config* cfg, vse_engine** out) {
 
 void vse_destroy(vse_engine* e) {
     if (!e) return;
+    cudaSetDevice(e->impl->cfg.device);
     delete e->impl;
     delete e;
 }
@@ -95,6 +99,11 @@ const char* vse_last_error(const vse_engine* e) { return e ? e->impl->last_error
 int vse_load_plan(vse_engine* e, int32_t which, const void* blob, size_t nbytes) {
     if (!e || !blob) return VSE_ERR_INVALID;
     return guarded(e, [&] { e->impl->load_plan(which, blob, nbytes); });
+}
+
+int vse_set_conv_input_ranges(vse_engine* e, int32_t which, const float* absmax, int32_t n_steps) {
+    if (!e || !absmax || n_steps < 0) return VSE_ERR_INVALID;
+    return guarded(e, [&] { e->impl->set_conv_input_ranges(which, absmax, n_steps); });
 }
 
 int vse_run(vse_engine* e, const uint8_t* const* frames, const int32_t* h, const int32_t* w, const int32_t* row_stride,

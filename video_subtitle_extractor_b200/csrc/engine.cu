@@ -5,6 +5,7 @@
 #include "fast_kernels.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,9 +59,27 @@ void Engine::load_plan(int which, const void* blob, size_t n) {
     plan_prec_[which] = cfg.precision;
     if (which == 0 && (cfg.flags & VSE_FLAG_DET_FP32)) plan_prec_[which] = VSE_PRECISION_FP32;
     if (which == 0 && (cfg.flags & VSE_FLAG_DET_TF32)) plan_prec_[which] = VSE_PRECISION_TF32;
-    if (plan_prec_[which] < VSE_PRECISION_FP16 || plan_prec_[which] > VSE_PRECISION_TF32) throw InvalidArg{"bad precision"};
+    if (plan_prec_[which] < VSE_PRECISION_FP16 || plan_prec_[which] > VSE_PRECISION_FP32_TC) throw InvalidArg{"bad precision"};
     prepare_plan(which, lp);
     lp.loaded = true;
+}
+
+// split mode (VSE_PRECISION_FP32_TC): per-step operand scale from calibrated input ranges — the power of two that brings the
+// largest expected |x| into [2^13, 2^14) (4x headroom below the fp16 limit 65504); see gemm_tc.cu, transform warps
+void Engine::set_conv_input_ranges(int which, const float* absmax, int n_steps) {
+    if (which < 0 || which > 1 || !plans_[which].loaded) throw StateError{"set_conv_input_ranges: plan not loaded"};
+    LoadedPlan& lp = plans_[which];
+    if (n_steps != int(lp.data.steps.size())) throw InvalidArg{"set_conv_input_ranges: one value per plan step expected"};
+    for (int k = 0; k < n_steps; k++) {
+        float s = tc_split_activation_scale();
+        if (absmax[k] > 0.f && std::isfinite(absmax[k])) {
+            int e = 0;
+            std::frexp(absmax[k], &e);                       // absmax = m * 2^e, m in [0.5, 1)
+            s = std::ldexp(1.f, std::max(-30, std::min(14, 14 - e)));
+        }
+        lp.a_scale[k] = s;
+    }
+    last_tab_[which].clear();                                // contexts cache the scale: rebuild on the next run
 }
 
 void Engine::prepare_plan(int which, LoadedPlan& lp) {
@@ -70,6 +89,7 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
     struct Off { size_t w_t = SIZE_MAX, bias_pk = SIZE_MAX, ps_pk = SIZE_MAX, pb_pk = SIZE_MAX, w = SIZE_MAX, bias = SIZE_MAX, ps = SIZE_MAX, pb = SIZE_MAX, g = SIZE_MAX, b = SIZE_MAX, sc = SIZE_MAX, sh = SIZE_MAX; };
     std::vector<Off> offs(pd.steps.size());
     lp.dev.assign(pd.steps.size(), StepDev{});
+    lp.a_scale.assign(pd.steps.size(), tc_split_activation_scale());
     auto alloc = [&](size_t nfloats) {
         size_t o = host.size();
         host.resize(o + round_up(int(nfloats), 4), 0.f);
@@ -211,7 +231,7 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
     lp.tcw_pk.assign(pd.steps.size(), TcWeights{});
     lp.tcw_pk_off.assign(pd.steps.size(), 0);
     if (plan_prec_[which] != VSE_PRECISION_FP32 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
-        const bool tf32 = plan_prec_[which] == VSE_PRECISION_TF32;
+        const int tc_mode = plan_prec_[which] == VSE_PRECISION_TF32 ? TC_TF32 : plan_prec_[which] == VSE_PRECISION_FP32_TC ? TC_SPLIT : TC_F16;
         std::vector<uint16_t> all;
         auto append = [&](TcWeights& t) -> size_t {
             while (all.size() % 512) all.push_back(0);   // 1024-byte aligned matrices
@@ -224,7 +244,7 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
         for (size_t k = 0; k < pd.steps.size(); k++) {
             const StepRec& s = pd.steps[k];
             if (s.op != OP_CONV || s.p[P_SH] != 1 || s.p[P_SW] != 1) continue;
-            lp.tcw[k] = tc_pack_weights(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], s.p[P_KH] * s.p[P_KW], tf32);
+            lp.tcw[k] = tc_pack_weights(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], s.p[P_KH] * s.p[P_KW], tc_mode);
             lp.tcw_off[k] = append(lp.tcw[k]);
             if (lp.dev[k].pack > 0) {
                 lp.tcw_pk[k] = tc_pack_weights_pixelpacked(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], value_cs(pd, s.ins[0]),
@@ -449,7 +469,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
     std::vector<int> fd(pd.values.size());
     for (size_t v = 0; v < pd.values.size(); v++) fd[v] = pd.values[v].first_def;
     cx.se_conv.assign(pd.steps.size(), 0);
-    if (!keep_all && plan_prec_[which] == VSE_PRECISION_FP16 &&
+    if (!keep_all && (plan_prec_[which] == VSE_PRECISION_FP16 || plan_prec_[which] == VSE_PRECISION_FP32_TC) &&
         !(cfg.flags & (VSE_FLAG_NO_FAST_KERNELS | VSE_FLAG_NO_TENSOR_CORES | VSE_FLAG_NO_SE_CONV))) {
         auto readers = [&](int vid) {
             int n = 0;
@@ -535,6 +555,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
                 const int64_t gpix = int64_t(i1 - i0) * gi.tab[i0].h * gi.tab[i0].w;
                 ok = tc_conv_setup(g.tc, base, value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], false, gpix, int(i1 - i0), gi.tab[i0].h,
                                    gi.tab[i0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX), !(cfg.flags & VSE_FLAG_NO_HALO)).empty();
+                g.tc.a_scale = lp.a_scale[k];
                 groups.push_back(std::move(g));
                 i0 = i1;
                 if (groups.size() > 64) ok = false;
@@ -549,6 +570,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
             std::string why = tc_conv_setup(cx.tc[k], vptr(which, s.ins[0]), 64, 64, wpk, lp.tcw_pk[k], true, gi.total / lp.dev[k].pack,
                                             cx.n_img, 1, 1, 1, 1, 0, 0, false);
             cx.tc[k].pack = why.empty() ? lp.dev[k].pack : 0;
+            cx.tc[k].a_scale = lp.a_scale[k];
             if (why.empty()) continue;
         }
         const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_off[k];
@@ -556,6 +578,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
                                         gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX),
                                         !(cfg.flags & VSE_FLAG_NO_HALO));
         if (!why.empty()) cx.tc[k].valid = false;
+        cx.tc[k].a_scale = lp.a_scale[k];
     }
 }
 
@@ -604,6 +627,9 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
     const PlanData& pd = lp.data;
     ExecContext& cx = ctx_[which];
     const int prec = plan_prec_[which] == VSE_PRECISION_FP16 ? 0 : 1;   // storage type of activations: __half / float
+    // the specialised kernels exist for fp16 storage and — as the same templates on float — for the fp32 tensor-core mode;
+    // VSE_PRECISION_FP32 / TF32 keep the generic kernels
+    const bool fast_ok = (prec == 0 || plan_prec_[which] == VSE_PRECISION_FP32_TC) && !(cfg.flags & VSE_FLAG_NO_FAST_KERNELS);
     const ImgTab* dtab = cx.tabs.as<ImgTab>();
     auto tab_of = [&](int vid) -> const ImgTab* {
         int g = cx.vals[vid].geo;
@@ -636,7 +662,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
         const ValueRec& vo = pd.values[s.out];
         const int out_f32 = vo.dtype == DT_F32 && vo.kind == KIND_IMG;
         // concat gather: a run of CHSCALE / plain nearest-UPSAMPLE steps filling slices of one concat buffer -> one kernel
-        if (prec == 0 && !(cfg.flags & (VSE_FLAG_NO_FAST_KERNELS | VSE_FLAG_NO_CONCAT_GATHER)) && vo.alias_of >= 0 &&
+        if (fast_ok && !(cfg.flags & VSE_FLAG_NO_CONCAT_GATHER) && vo.alias_of >= 0 &&
             (s.op == OP_CHSCALE || (s.op == OP_UPSAMPLE && !s.p[P_HAS_ADD]))) {
             GatherSrc src[4];
             int n = 0;
@@ -650,7 +676,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 for (size_t q = k; q < j; q++) dep = dep || sj.ins[0] == pd.steps[q].out || sj.ins[1] == pd.steps[q].out;
                 if (dep) break;
                 GatherSrc& g = src[n++];
-                g.in = static_cast<const __half*>(ptr_of(sj.ins[0]));
+                g.in = ptr_of(sj.ins[0]);
                 g.in_cs = value_cs(pd, sj.ins[0]);
                 g.tin = tab_of(sj.ins[0]);
                 g.scale_px = sj.op == OP_UPSAMPLE ? sj.p[P_SCALE] : 1;
@@ -658,15 +684,15 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 g.scale = sj.op == OP_CHSCALE ? static_cast<const float*>(ptr_of(sj.ins[1])) : nullptr;
                 g.scale_c = sj.op == OP_CHSCALE ? pd.values[sj.ins[1]].channels : 0;
                 g.residual = sj.op == OP_CHSCALE ? sj.p[P_RESIDUAL] : 0;
-                g.out = static_cast<__half*>(ptr_of(sj.out));
+                g.out = ptr_of(sj.out);
                 g.out_cs = value_cs(pd, sj.out);
                 g.cvecs = pad8(vj.channels) / 8;
             }
             if (n >= 2) {
-                std::sort(src, src + n, [](const GatherSrc& a, const GatherSrc& b) { return a.out < b.out; });
+                std::sort(src, src + n, [](const GatherSrc& a, const GatherSrc& b) { return static_cast<const char*>(a.out) < static_cast<const char*>(b.out); });
                 int mh = 0, mw = 0;
                 for (const ImgTab& t : geo_of(s.out).tab) { mh = std::max(mh, t.h); mw = std::max(mw, t.w); }
-                launch_concat_gather(src, n, tab_of(s.out), cx.n_img, mh, mw, stream);
+                launch_concat_gather(src, n, tab_of(s.out), cx.n_img, mh, mw, stream, prec);
                 launches++;
                 cx.kind[k] = 2;
                 for (size_t q = k + 1; q < j; q++) {
@@ -698,7 +724,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 a.kh = s.p[P_KH]; a.kw = s.p[P_KW]; a.sh = s.p[P_SH]; a.sw = s.p[P_SW]; a.ph = s.p[P_PH]; a.pw = s.p[P_PW];
                 a.out_f32 = out_f32;
                 for (int i = 0; i < 3; i++) { a.nscale[i] = pd.hdr.norm_scale[i]; a.nshift[i] = pd.hdr.norm_shift[i]; }
-                const bool fast = prec == 0 && !(cfg.flags & VSE_FLAG_NO_FAST_KERNELS);
+                const bool fast = fast_ok;
                 auto max_units = [&](int tw) {   // max over images of out_h * ceil(out_w / tw)
                     int m = 0;
                     for (const ImgTab& t : geo_of(s.out).tab) m = std::max(m, t.h * ((t.w + tw - 1) / tw));
@@ -713,9 +739,9 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                     int mh = 0, mw = 0;
                     for (const ImgTab& t : geo_of(s.out).tab) { mh = std::max(mh, t.h); mw = std::max(mw, t.w); }
                     const bool use_reg = dw_mode == 2 || (dw_mode == 3 && a.cin_pad >= dw_reg_min_c);
-                    if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && use_reg && launch_dwconv_reg(a, mh, mw, stream)) cx.kind[k] = 2;
-                    else if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && dw_mode >= 1 && launch_dwconv_tiled(a, mh, mw, stream)) cx.kind[k] = 2;
-                    else if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
+                    if (fast && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && (use_reg || prec == 1) && launch_dwconv_reg(a, mh, mw, stream, prec)) cx.kind[k] = 2;
+                    else if (fast && prec == 0 && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && dw_mode >= 1 && launch_dwconv_tiled(a, mh, mw, stream)) cx.kind[k] = 2;
+                    else if (fast && prec == 0 && !(cfg.flags & VSE_FLAG_NO_FAST_DW) && launch_dwconv_fast(a, max_units(4), stream)) cx.kind[k] = 2;
                     else launch_dwconv(a, prec, stream);
                 } else if (s.op == OP_DECONV2) {
                     // DB head: deconv(C->C)+ReLU feeding only a deconv(C->1)+sigmoid that is a fetched fp32 map -> one kernel
@@ -731,7 +757,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                             const StepDev& d2 = lp.dev[k + 1];
                             fused = launch_db_head_fused(a.in, a.in_cs, s.p[P_CIN], d.w, d.bias, d2.w, d2.bias,
                                                          static_cast<float*>(ptr_of(s2.out)), value_cs(pd, s2.out), a.tin,
-                                                         tab_of(s2.out), cx.n_img, geo_of(s.ins[0]).max_pix, stream);
+                                                         tab_of(s2.out), cx.n_img, geo_of(s.ins[0]).max_pix, stream, prec);
                         }
                     }
                     if (fused) {
@@ -742,7 +768,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                     } else {
                         launch_deconv2(a, s.p[P_COUT], prec, stream);
                     }
-                } else if (s.op == OP_STEM && fast && !(cfg.flags & VSE_FLAG_NO_FAST_STEM) && launch_stem_fast(a, s.p[P_COUT], max_units(2), stream)) {
+                } else if (s.op == OP_STEM && fast && !(cfg.flags & VSE_FLAG_NO_FAST_STEM) && launch_stem_fast(a, s.p[P_COUT], max_units(2), stream, prec)) {
                     cx.kind[k] = 2;
                 } else if (s.op == OP_CONV && cx.se_conv[k] && cx.tc[k].valid) {
                     // fused residual squeeze-excite (see build_context): pool the conv INPUT, gate from W mean(x) + b, conv
@@ -788,7 +814,7 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 float* partial = reinterpret_cast<float*>(static_cast<char*>(arena_[which].p) + cx.scratch_off);
                 // squeeze-excite: GPOOL -> VECLIN -> VECLIN (each the sole consumer of the previous) -> one gate kernel
                 bool fused = false;
-                if (prec == 0 && !(cfg.flags & (VSE_FLAG_NO_FAST_KERNELS | VSE_FLAG_NO_SE_FUSION)) && !last_keep_all_[which] && k + 2 < pd.steps.size()) {
+                if (fast_ok && !(cfg.flags & VSE_FLAG_NO_SE_FUSION) && !last_keep_all_[which] && k + 2 < pd.steps.size()) {
                     const StepRec& f1 = pd.steps[k + 1];
                     const StepRec& f2 = pd.steps[k + 2];
                     auto plain = [](const StepRec& f) { return !f.p[P_HAS_POST] && !f.p[P_HAS_RES] && f.p[P_ACT2] == ACT_NONE; };

@@ -121,6 +121,7 @@ struct LoadedPlan {
     std::vector<TcWeights> tcw_pk;   // pixel-packed block-diagonal variants (n_chunk == 0 => none)
     std::vector<size_t> tcw_pk_off;
     DevBuf tc_weights;
+    std::vector<float> a_scale;      // per step: power of two applied to a convolution's operand rows in split mode
     bool loaded = false;
 };
 
@@ -150,6 +151,7 @@ class Engine {
     explicit Engine(const vse_config& cfg);
     ~Engine();
     void load_plan(int which, const void* blob, size_t n);
+    void set_conv_input_ranges(int which, const float* absmax, int n_steps);
 
     // Builds geometry + memory plan for `which` on images (h, w[i], valid_w[i]) and runs it.
     // Input pixels (uint8 BGRX) must already be in `input_dev` laid out image after image.

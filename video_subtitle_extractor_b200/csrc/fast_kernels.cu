@@ -40,6 +40,36 @@ __device__ __forceinline__ void store8h(__half* p, const float* v) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
+// storage-generic 8-channel vectors: fp16 activations (16 bytes) or fp32 activations (32 bytes)
+template <typename T> __device__ __forceinline__ void load8(const T* p, float* v);
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float* v) { load8h(p, v); }
+template <> __device__ __forceinline__ void load8<float>(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float* v);
+template <> __device__ __forceinline__ void store8<__half>(__half* p, const float* v) { store8h(p, v); }
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// one channel PAIR of a pixel: a packed half2 word or a float2
+template <typename T> struct PairOf;
+template <> struct PairOf<__half> {
+    typedef unsigned raw;
+    static __device__ __forceinline__ raw zero() { return 0u; }
+    static __device__ __forceinline__ raw ld(const char* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+    static __device__ __forceinline__ float2 f2(raw r) { return __half22float2(*reinterpret_cast<const __half2*>(&r)); }
+    static __device__ __forceinline__ void st(char* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
+};
+template <> struct PairOf<float> {
+    typedef float2 raw;
+    static __device__ __forceinline__ raw zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ raw ld(const char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+    static __device__ __forceinline__ float2 f2(raw r) { return r; }
+    static __device__ __forceinline__ void st(char* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+
 template <int ACT>
 __device__ __forceinline__ float fact(float x) {
     if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
@@ -364,8 +394,9 @@ __device__ __forceinline__ float2 fact2(float2 v) {
     } else return v;
 }
 
-template <int K, int SH, int SW, int TH, int TW, int ACT>
-__global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x, int tiles_y) {
+template <typename T, int K, int SH, int SW, int TH, int TW, int ACT>
+__global__ void __launch_bounds__(128, sizeof(T) == 2 ? 3 : 2) dwconv_reg_kernel(DwDev p, int tiles_x, int tiles_y) {
+    typedef PairOf<T> PR;
     constexpr int IH = (TH - 1) * SH + K, IW = (TW - 1) * SW + K;
     const int img = blockIdx.y;
     const int cp2 = p.cvecs * 4;                          // channel pairs per pixel
@@ -397,13 +428,13 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
     if (oy0 >= to.h || ox0 >= to.w) return;
     const int c0 = pair * 2;
     const int iy0 = oy0 * SH - p.ph, ix0 = ox0 * SW - p.pw;
-    const char* base = reinterpret_cast<const char*>(p.in + size_t(ti.off) * p.in_cs + c0);
-    const unsigned cstep = unsigned(p.in_cs) * 2u;        // bytes per pixel
+    const char* base = reinterpret_cast<const char*>(reinterpret_cast<const T*>(p.in) + size_t(ti.off) * p.in_cs + c0);
+    const unsigned cstep = unsigned(p.in_cs) * unsigned(sizeof(T));        // bytes per pixel
     // The whole input patch goes into registers first (packed half2, one register per tap): all IH*IW loads of a thread
     // are in flight together, so a thread pays ONE memory round trip instead of one per patch row — on these small,
     // L2-resident maps the dependent round trips were half the run time of the row-by-row variants.  Every address is one
     // IMAD.WIDE.  Out-of-image taps are predicated loads that yield 0 (the FMAs then add +0).
-    unsigned xin[IH][IW];
+    typename PR::raw xin[IH][IW];
     const bool interior = iy0 >= 0 && iy0 + IH <= ti.h && ix0 >= 0 && ix0 + IW <= ti.w;
     if (interior) {
         const char* pp = addr_mad(base, unsigned(iy0 * ti.w + ix0), cstep);
@@ -412,7 +443,7 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
         for (int r = 0; r < IH; r++) {
             const char* rowp = addr_mad(pp, unsigned(r), rstep);
 #pragma unroll
-            for (int i = 0; i < IW; i++) xin[r][i] = __ldg(reinterpret_cast<const unsigned*>(addr_mad(rowp, unsigned(i), cstep)));
+            for (int i = 0; i < IW; i++) xin[r][i] = PR::ld(addr_mad(rowp, unsigned(i), cstep));
         }
     } else {
 #pragma unroll
@@ -423,8 +454,8 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
 #pragma unroll
             for (int i = 0; i < IW; i++) {
                 const int ix = ix0 + i;
-                unsigned v = 0u;
-                if (row_ok && ix >= 0 && ix < ti.w) v = __ldg(reinterpret_cast<const unsigned*>(addr_mad(base, unsigned(roff + ix), cstep)));
+                typename PR::raw v = PR::zero();
+                if (row_ok && ix >= 0 && ix < ti.w) v = PR::ld(addr_mad(base, unsigned(roff + ix), cstep));
                 xin[r][i] = v;
             }
         }
@@ -438,7 +469,7 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
     for (int r = 0; r < IH; r++) {
         float2 x[IW];
 #pragma unroll
-        for (int i = 0; i < IW; i++) x[i] = __half22float2(*reinterpret_cast<const __half2*>(&xin[r][i]));
+        for (int i = 0; i < IW; i++) x[i] = PR::f2(xin[r][i]);
 #pragma unroll
         for (int a = 0; a < TH; a++) {
             const int ky = r - a * SH;   // compile-time after unrolling
@@ -453,8 +484,8 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
             }
         }
     }
-    char* obase = reinterpret_cast<char*>(p.out + (size_t(to.off) + size_t(oy0) * to.w + ox0) * p.out_cs + c0);
-    const unsigned ocstep = unsigned(p.out_cs) * 2u, orstep = unsigned(to.w) * ocstep;
+    char* obase = reinterpret_cast<char*>(reinterpret_cast<T*>(p.out) + (size_t(to.off) + size_t(oy0) * to.w + ox0) * p.out_cs + c0);
+    const unsigned ocstep = unsigned(p.out_cs) * unsigned(sizeof(T)), orstep = unsigned(to.w) * ocstep;
     const bool full = oy0 + TH <= to.h && ox0 + TW <= to.w;
 #pragma unroll
     for (int a = 0; a < TH; a++) {
@@ -465,43 +496,57 @@ __global__ void __launch_bounds__(128, 3) dwconv_reg_kernel(DwDev p, int tiles_x
             if (!full && ox0 + b >= to.w) break;
             float2 v = fact2<ACT>(fadd2(acc[a][b], bias));
             if (post) v = ffma2(v, sc, sh);
-            *reinterpret_cast<__half2*>(const_cast<char*>(addr_mad(orow, unsigned(b), ocstep))) = __floats2half2_rn(v.x, v.y);
+            PR::st(const_cast<char*>(addr_mad(orow, unsigned(b), ocstep)), v);
         }
     }
 }
 
-template <int K, int SH, int SW, int TH, int TW>
+template <typename T, int K, int SH, int SW, int TH, int TW>
 static bool dw_reg_launch(const DwDev& d, const ConvArgs& a, int max_h, int max_w, cudaStream_t st) {
     const int tiles_x = (max_w + TW - 1) / TW, tiles_y = (max_h + TH - 1) / TH;
     if (int64_t(tiles_x) * tiles_y * d.cvecs * 4 > 0x7fffff00LL) return false;
-    if (int64_t(max_w) * std::max(SW, 1) * std::max(a.in_cs, a.out_cs) * 2 * 2 > 0x7fffffffLL) return false;   // 32-bit row strides
+    if (int64_t(max_w) * std::max(SW, 1) * std::max(a.in_cs, a.out_cs) * int(sizeof(T)) * 2 > 0x7fffffffLL) return false;   // 32-bit row strides
     dim3 grid(cdiv_i(int64_t(tiles_x) * tiles_y * d.cvecs * 4, 128), a.n_img);
     switch (a.epi.act) {
-        case ACT_NONE: pdl_launch(dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_NONE>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
-        case ACT_RELU: pdl_launch(dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_RELU>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
-        case ACT_HSWISH: pdl_launch(dwconv_reg_kernel<K, SH, SW, TH, TW, ACT_HSWISH>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
+        case ACT_NONE: pdl_launch(dwconv_reg_kernel<T, K, SH, SW, TH, TW, ACT_NONE>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
+        case ACT_RELU: pdl_launch(dwconv_reg_kernel<T, K, SH, SW, TH, TW, ACT_RELU>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
+        case ACT_HSWISH: pdl_launch(dwconv_reg_kernel<T, K, SH, SW, TH, TW, ACT_HSWISH>, grid, 128, 0, st, d, tiles_x, tiles_y); return true;
         default: return false;
     }
 }
 
-bool launch_dwconv_reg(const ConvArgs& a, int max_out_h, int max_out_w, cudaStream_t st) {
+bool launch_dwconv_reg(const ConvArgs& a, int max_out_h, int max_out_w, cudaStream_t st, int prec) {
     if (a.epi.res || a.epi.act2 != ACT_NONE || a.out_f32 || a.kh != a.kw) return false;
     if (2 * a.ph != a.kh - 1 || 2 * a.pw != a.kw - 1) return false;
     DwDev d{static_cast<const __half*>(a.in), static_cast<__half*>(a.out), a.w, a.epi.bias, a.epi.post_scale, a.epi.post_shift,
             a.tin, a.tout, a.in_cs, a.out_cs, a.cin_pad / 8, a.cin_pad, a.ph, a.pw};
     if (!d.bias) return false;
+    if (prec == 1) {
+        // fp32 activations: a channel pair is a float2 (two registers per tap), so the tiles are smaller
+        switch (a.kh * 100 + a.sh * 10 + a.sw) {
+            case 311: return dw_reg_launch<float, 3, 1, 1, 4, 4>(d, a, max_out_h, max_out_w, st);
+            case 322: return dw_reg_launch<float, 3, 2, 2, 3, 4>(d, a, max_out_h, max_out_w, st);
+            case 321: return dw_reg_launch<float, 3, 2, 1, 3, 4>(d, a, max_out_h, max_out_w, st);
+            case 312: return dw_reg_launch<float, 3, 1, 2, 4, 3>(d, a, max_out_h, max_out_w, st);
+            case 511: return dw_reg_launch<float, 5, 1, 1, 2, 4>(d, a, max_out_h, max_out_w, st);
+            case 522: return dw_reg_launch<float, 5, 2, 2, 2, 3>(d, a, max_out_h, max_out_w, st);
+            case 521: return dw_reg_launch<float, 5, 2, 1, 2, 4>(d, a, max_out_h, max_out_w, st);
+            case 512: return dw_reg_launch<float, 5, 1, 2, 2, 3>(d, a, max_out_h, max_out_w, st);
+            default: return false;
+        }
+    }
     // rows per tile: 3 or 4, whichever pads the tallest image less (ties: 4)
     const bool th3 = ((max_out_h + 2) / 3) * 3 < ((max_out_h + 3) / 4) * 4;
     const int key = a.kh * 100 + a.sh * 10 + a.sw;
 #define VSE_DW_REG(KK, SHH, SWW) \
-    (th3 ? dw_reg_launch<KK, SHH, SWW, 3, 4>(d, a, max_out_h, max_out_w, st) : dw_reg_launch<KK, SHH, SWW, 4, 4>(d, a, max_out_h, max_out_w, st))
+    (th3 ? dw_reg_launch<__half, KK, SHH, SWW, 3, 4>(d, a, max_out_h, max_out_w, st) : dw_reg_launch<__half, KK, SHH, SWW, 4, 4>(d, a, max_out_h, max_out_w, st))
     switch (key) {
         case 311: return VSE_DW_REG(3, 1, 1);
         case 322: return VSE_DW_REG(3, 2, 2);
         case 321: return VSE_DW_REG(3, 2, 1);
         case 312: return VSE_DW_REG(3, 1, 2);
         case 511: return VSE_DW_REG(5, 1, 1);
-        case 522: return dw_reg_launch<5, 2, 2, 2, 4>(d, a, max_out_h, max_out_w, st);   // 7 x 11 patch: the 4-row tile (11 x 11) would spill
+        case 522: return dw_reg_launch<__half, 5, 2, 2, 2, 4>(d, a, max_out_h, max_out_w, st);   // 7 x 11 patch: the 4-row tile (11 x 11) would spill
         case 521: return VSE_DW_REG(5, 2, 1);
         case 512: return VSE_DW_REG(5, 1, 2);
         default: return false;
@@ -518,7 +563,7 @@ struct StemDev {
     float nscale[3], nshift[3];
 };
 
-template <int ACT>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
@@ -593,22 +638,30 @@ __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
             v[2 * j] = fact<ACT>(acc[t][j].x);
             v[2 * j + 1] = fact<ACT>(acc[t][j].y);
         }
-        __half* o = p.out + (size_t(to.off) + size_t(oy) * to.w + ox) * p.out_cs;
-        store8h(o, v);
-        store8h(o + 8, v + 8);
+        T* o = reinterpret_cast<T*>(p.out) + (size_t(to.off) + size_t(oy) * to.w + ox) * p.out_cs;
+        store8<T>(o, v);
+        store8<T>(o + 8, v + 8);
     }
 }
 
-bool launch_stem_fast(const ConvArgs& a, int cout, int max_out_pix_pairs, cudaStream_t st) {
+bool launch_stem_fast(const ConvArgs& a, int cout, int max_out_pix_pairs, cudaStream_t st, int prec) {
     if (!a.in_u8 || a.kh != 3 || a.kw != 3 || a.sh != 2 || a.sw != 2 || a.ph != 1 || a.pw != 1 || cout != 16 || a.out_f32) return false;
     if (a.epi.res || a.epi.post_scale || a.epi.act2 != ACT_NONE || !a.epi.bias || a.out_cs < 16) return false;
     StemDev d{static_cast<const unsigned char*>(a.in), static_cast<__half*>(a.out), a.w, a.epi.bias, a.tin, a.tout,
               a.out_cs, a.w_ci, a.w_co, a.epi.act, {a.nscale[0], a.nscale[1], a.nscale[2]}, {a.nshift[0], a.nshift[1], a.nshift[2]}};
     dim3 grid(cdiv_i(max_out_pix_pairs, 128), a.n_img);
+    if (prec == 1) {
+        switch (a.epi.act) {
+            case ACT_NONE: pdl_launch(stem_fast_kernel<float, ACT_NONE>, grid, 128, 0, st, d); return true;
+            case ACT_RELU: pdl_launch(stem_fast_kernel<float, ACT_RELU>, grid, 128, 0, st, d); return true;
+            case ACT_HSWISH: pdl_launch(stem_fast_kernel<float, ACT_HSWISH>, grid, 128, 0, st, d); return true;
+            default: return false;
+        }
+    }
     switch (a.epi.act) {
-        case ACT_NONE: pdl_launch(stem_fast_kernel<ACT_NONE>, grid, 128, 0, st, d); return true;
-        case ACT_RELU: pdl_launch(stem_fast_kernel<ACT_RELU>, grid, 128, 0, st, d); return true;
-        case ACT_HSWISH: pdl_launch(stem_fast_kernel<ACT_HSWISH>, grid, 128, 0, st, d); return true;
+        case ACT_NONE: pdl_launch(stem_fast_kernel<__half, ACT_NONE>, grid, 128, 0, st, d); return true;
+        case ACT_RELU: pdl_launch(stem_fast_kernel<__half, ACT_RELU>, grid, 128, 0, st, d); return true;
+        case ACT_HSWISH: pdl_launch(stem_fast_kernel<__half, ACT_HSWISH>, grid, 128, 0, st, d); return true;
         default: return false;
     }
 }
@@ -623,7 +676,7 @@ struct HeadDev {
     int in_cs;
 };
 
-template <int C>
+template <typename T, int C>
 __global__ void __launch_bounds__(128, 4) db_head_fused_kernel(HeadDev p) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
@@ -641,9 +694,9 @@ __global__ void __launch_bounds__(128, 4) db_head_fused_kernel(HeadDev p) {
     if (idx >= ti.h * ti.w) return;
     const int iy = idx / ti.w, ix = idx - iy * ti.w;
     float x[C];
-    const __half* ip = p.in + (size_t(ti.off) + idx) * p.in_cs;
+    const T* ip = reinterpret_cast<const T*>(p.in) + (size_t(ti.off) + idx) * p.in_cs;
 #pragma unroll
-    for (int c = 0; c < C; c += 8) load8h(ip + c, x + c);
+    for (int c = 0; c < C; c += 8) load8<T>(ip + c, x + c);
     float o[4][4];   // [row 2*dy1+dy2][col 2*dx1+dx2]
 #pragma unroll
     for (int pos1 = 0; pos1 < 4; pos1++) {
@@ -683,12 +736,13 @@ __global__ void __launch_bounds__(128, 4) db_head_fused_kernel(HeadDev p) {
 
 bool launch_db_head_fused(const void* in, int in_cs, int c, const float* w1, const float* b1, const float* w2, const float* b2,
                           float* out, int out_cs, const ImgTab* tin, const ImgTab* tout, int n_img, int max_in_pix,
-                          cudaStream_t st) {
+                          cudaStream_t st, int prec) {
     if (c != 24 || out_cs != 1 || (in_cs & 7) || !b1 || !b2) return false;
     if (reinterpret_cast<uintptr_t>(out) & 15) return false;
     HeadDev d{static_cast<const __half*>(in), out, w1, b1, w2, b2, tin, tout, in_cs};
     dim3 grid(cdiv_i(max_in_pix, 128), n_img);
-    pdl_launch(db_head_fused_kernel<24>, grid, 128, 0, st, d);
+    if (prec == 1) pdl_launch(db_head_fused_kernel<float, 24>, grid, 128, 0, st, d);
+    else pdl_launch(db_head_fused_kernel<__half, 24>, grid, 128, 0, st, d);
     return true;
 }
 
@@ -797,6 +851,7 @@ struct GatherDev {
     const ImgTab* tout;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(256) concat_gather_kernel(GatherDev p) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
@@ -814,7 +869,7 @@ __global__ void __launch_bounds__(256) concat_gather_kernel(GatherDev p) {
     const ImgTab ti = g.tin[img];
     const int iy = g.shift >= 0 ? oy >> g.shift : oy / g.scale_px, ix = g.shift >= 0 ? ox >> g.shift : ox / g.scale_px;
     float x[8];
-    load8h(g.in + (size_t(ti.off) + size_t(iy) * ti.w + ix) * g.in_cs + piece * 8, x);
+    load8<T>(reinterpret_cast<const T*>(g.in) + (size_t(ti.off) + size_t(iy) * ti.w + ix) * g.in_cs + piece * 8, x);
     if (g.scale) {
         const float* sp = g.scale + size_t(img) * g.scale_c;
 #pragma unroll
@@ -824,10 +879,11 @@ __global__ void __launch_bounds__(256) concat_gather_kernel(GatherDev p) {
             x[j] = g.residual ? x[j] + x[j] * sc : x[j] * sc;
         }
     }
-    store8h(g.out + (size_t(to.off) + size_t(oy) * to.w + ox) * g.out_cs + piece * 8, x);
+    store8<T>(reinterpret_cast<T*>(g.out) + (size_t(to.off) + size_t(oy) * to.w + ox) * g.out_cs + piece * 8, x);
 }
 
-void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_h, int max_out_w, cudaStream_t st) {
+void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n_img, int max_out_h, int max_out_w, cudaStream_t st,
+                          int prec) {
     GatherDev d{};
     d.n = n;
     d.tout = tout;
@@ -840,7 +896,8 @@ void launch_concat_gather(const GatherSrc* src, int n, const ImgTab* tout, int n
         d.s[i].shift = sh;
     }
     dim3 grid(cdiv_i(int64_t(max_out_w) * d.total_cvecs, 256), max_out_h, n_img);
-    pdl_launch(concat_gather_kernel, grid, 256, 0, st, d);
+    if (prec == 1) pdl_launch(concat_gather_kernel<float>, grid, 256, 0, st, d);
+    else pdl_launch(concat_gather_kernel<__half>, grid, 256, 0, st, d);
 }
 
 }  // namespace vse

@@ -17,6 +17,7 @@
 
 #include <cuda_fp16.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -27,10 +28,13 @@ namespace vse {
 static constexpr int BLOCK_M = 128, BLOCK_K = 64;   // BLOCK_K: fp16 elements per 128-byte K row (32 for fp32 / tf32)
 static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 static constexpr int kEpiWarps = 8;
-static constexpr int kThreads = 64 + 32 * kEpiWarps;
+static constexpr int kXfWarps = 4;              // split mode: warps that turn fp32 operand rows into fp16 hi | lo in place
+static constexpr int kThreadsBase = 64 + 32 * kEpiWarps;
+static constexpr int kThreads = kThreadsBase + 32 * kXfWarps;   // launch bound; plain fp16 / tf32 launches use kThreadsBase
 static constexpr int kMaxAccStages = 8;         // TMEM accumulator ring (512 columns / n_chunk, at most 8)
 static constexpr int kBarRegion = 512;          // shared-memory bytes reserved for the mbarriers + TMEM slot
 static constexpr int kBResidentMax = 80 * 1024; // weight matrices up to this size stay in shared memory for the whole kernel
+static constexpr int kBResidentMaxSplit = 112 * 1024;   // split mode: hi | lo weights are twice the bytes, the staging ring shrinks instead
 static constexpr int kOutBufs = 4;               // ring of [128 rows x 128 B] staging tiles for the TMA stores
 static constexpr int kOutBufBytes = BLOCK_M * 128;
 static constexpr int kParamSmemMaxCh = 1024;   // bias/scale/shift of up to this many channels are staged in shared memory
@@ -38,7 +42,7 @@ static constexpr int kMaxSmem = 227 * 1024;
 
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
-        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems;
+        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems, split, kbb, out_bufs;
     void* out;
     int out_cs;
     const float* bias;
@@ -49,6 +53,8 @@ struct TcParams {
     float hs_slope, hs_offset;
     const float* gate;   // optional per-image channel gate (fused squeeze-excite): v += v * gate[row / gate_rows][channel]
     int gate_c, gate_rows;
+    float a_scale;     // split mode: operand rows are multiplied by this power of two before the fp16 split (see transform warps)
+    float acc_scale;   // accumulator -> output units (1 / (a_scale * weight scale); 1 outside split mode)
     int n_total;       // n_chunks * n_chunk (bias / post arrays are readable up to here)
     int param_smem;    // 1: bias/scale/shift staged in shared memory
 };
@@ -283,7 +289,7 @@ struct EpiRegs {
     uint32_t pb_s, ps_s, pt_s;     // the same as shared-memory addresses when they are staged there (PSM)
     const void* res;
     int res_cs, n_store, act, act2, gate_c;
-    float hs_slope, hs_offset;
+    float hs_slope, hs_offset, acc_scale;
 };
 
 // per-channel constants: PSM = staged in shared memory -> ld.shared (the generic loads the compiler has to emit for a
@@ -309,8 +315,9 @@ __device__ __forceinline__ void epi_chunk16(const EpiRegs& e, const uint32_t* ra
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
         const float4 b = ld_const4<PSM>(e.pb, e.pb_s, cb + 4 * j4);
-        float x0 = __uint_as_float(raw[4 * j4 + 0]) + b.x, x1 = __uint_as_float(raw[4 * j4 + 1]) + b.y;
-        float x2 = __uint_as_float(raw[4 * j4 + 2]) + b.z, x3 = __uint_as_float(raw[4 * j4 + 3]) + b.w;
+        // acc * acc_scale + bias: acc_scale is 1 outside split mode (one rounding either way: identical to acc + bias)
+        float x0 = fmaf(__uint_as_float(raw[4 * j4 + 0]), e.acc_scale, b.x), x1 = fmaf(__uint_as_float(raw[4 * j4 + 1]), e.acc_scale, b.y);
+        float x2 = fmaf(__uint_as_float(raw[4 * j4 + 2]), e.acc_scale, b.z), x3 = fmaf(__uint_as_float(raw[4 * j4 + 3]), e.acc_scale, b.w);
         if constexpr (ACT >= 0) {
             x0 = act_t<ACT>(x0, e.hs_slope, e.hs_offset); x1 = act_t<ACT>(x1, e.hs_slope, e.hs_offset);
             x2 = act_t<ACT>(x2, e.hs_slope, e.hs_offset); x3 = act_t<ACT>(x3, e.hs_slope, e.hs_offset);
@@ -378,12 +385,13 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
     e.pb = pb; e.ps = ps; e.pt = pt;
     e.pb_s = PSM ? smem_u32(pb) : 0u; e.ps_s = PSM ? smem_u32(ps) : 0u; e.pt_s = PSM ? smem_u32(pt) : 0u;
     e.res = p.res; e.res_cs = p.res_cs; e.n_store = p.n_store; e.act = p.act; e.act2 = p.act2; e.gate_c = p.gate_c;
-    e.hs_slope = p.hs_slope; e.hs_offset = p.hs_offset;
+    e.hs_slope = p.hs_slope; e.hs_offset = p.hs_offset; e.acc_scale = p.acc_scale;
     const int row = q * 32 + lane;
     const int total_tiles = p.num_m_tiles * p.n_chunks;
     constexpr int SUBC = OUTF32 ? 32 : 64;        // columns per 128-byte staging row
     const int n_sub = (p.n_chunk + SUBC - 1) / SUBC;
     const uint32_t sout_addr = smem_u32(sout);
+    const int out_bufs = p.out_bufs;
     int acc = 0, slot = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -445,9 +453,12 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                 if (p.spatial) tma_store_4d(map_o, src, ch0 + sub * SUBC, x0, y0, img);
                 else tma_store_2d(map_o, src, ch0 + sub * SUBC, m_tile * BLOCK_M);
                 tma_store_commit();
-                tma_store_wait_read<kOutBufs - 2>();   // the tile written two barriers from now is free again (see ring note)
+                // the tile written two barriers from now is free again (see ring note); shorter rings wait for more stores
+                if (out_bufs >= 4) tma_store_wait_read<2>();
+                else if (out_bufs == 3) tma_store_wait_read<1>();
+                else tma_store_wait_read<0>();
             }
-            if (++slot == kOutBufs) slot = 0;
+            if (++slot == out_bufs) slot = 0;
         }
         tc_fence_before();
         __syncwarp();
@@ -466,23 +477,27 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUten
                                                   uint64_t* tmem_full, uint64_t* tmem_empty, const float* pb, const float* ps,
                                                   const float* pt, int q, int half, int lane, bool issuer) {
 #define VSE_EPI_ARGS p, map_o, sout, tmem_base, tmem_full, tmem_empty, pb, ps, pt, q, half, lane, issuer
+    const bool of32 = p.tf32 || p.split;   // fp32 activations in, fp32 out
     if (!p.param_smem || (p.gate && (POST || p.tf32 || p.act != ACT_NONE))) {
         if (p.gate) {   // not produced by the engine; kept correct rather than fast
-            if (p.tf32) epilogue_loop<-1, POST, true, false, true>(VSE_EPI_ARGS);
+            if (of32) epilogue_loop<-1, POST, true, false, true>(VSE_EPI_ARGS);
             else epilogue_loop<-1, POST, false, false, true>(VSE_EPI_ARGS);
         } else {
-            if (p.tf32) epilogue_loop<-1, POST, true, false, false>(VSE_EPI_ARGS);
+            if (of32) epilogue_loop<-1, POST, true, false, false>(VSE_EPI_ARGS);
             else epilogue_loop<-1, POST, false, false, false>(VSE_EPI_ARGS);
         }
         return;
     }
     if (p.gate) {
-        if constexpr (!POST) epilogue_loop<ACT_NONE, false, false, true, true>(VSE_EPI_ARGS);
+        if constexpr (!POST) {
+            if (of32) epilogue_loop<ACT_NONE, false, true, true, true>(VSE_EPI_ARGS);
+            else epilogue_loop<ACT_NONE, false, false, true, true>(VSE_EPI_ARGS);
+        }
         return;
     }
 #define VSE_EPI(A)                                                                  \
     do {                                                                            \
-        if (p.tf32) epilogue_loop<A, POST, true, true, false>(VSE_EPI_ARGS);        \
+        if (of32) epilogue_loop<A, POST, true, true, false>(VSE_EPI_ARGS);          \
         else epilogue_loop<A, POST, false, true, false>(VSE_EPI_ARGS);              \
     } while (0)
     switch (p.act) {
@@ -506,7 +521,27 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUten
 // 2: halo box, KH x KW taps per tile) with the common 3x3 shapes unrolled (KH / KW = 0: run-time extents), and every
 // per-iteration quantity is a running sum instead of a product.
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int KH_, int KW_, bool TF32>
+// one k-block of one filter tap: up to four K = 32-byte MMAs — or, in split mode, the six MMAs of the 3-term product: the
+// operand row is [hi(32 ch) | lo(32 ch)] (fp16, written in place by the transform warps), the weight row [Wh(32) | Wl(32)]:
+//   hi * Wh (2 MMAs), lo * Wh (2), hi * Wl (2); lo * Wl (2^-22 relative) is dropped.
+template <bool TF32, bool SPLIT>
+__device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a, uint32_t a_hi, uint32_t b, uint32_t idesc, uint32_t acc_first, int ks) {
+    if constexpr (SPLIT) {
+        umma_f16_words2(d_tmem, a, a_hi, b, idesc, acc_first);
+        umma_f16_words2(d_tmem, a + 2, a_hi, b + 2, idesc, 1u);
+        umma_f16_words2(d_tmem, a + 4, a_hi, b, idesc, 1u);
+        umma_f16_words2(d_tmem, a + 6, a_hi, b + 2, idesc, 1u);
+        umma_f16_words2(d_tmem, a, a_hi, b + 4, idesc, 1u);
+        umma_f16_words2(d_tmem, a + 2, a_hi, b + 6, idesc, 1u);
+    } else {
+        umma_words<TF32>(d_tmem, a, a_hi, b, idesc, acc_first);
+        if (ks > 1) umma_words<TF32>(d_tmem, a + 2, a_hi, b + 2, idesc, 1u);
+        if (ks > 2) umma_words<TF32>(d_tmem, a + 4, a_hi, b + 4, idesc, 1u);
+        if (ks > 3) umma_words<TF32>(d_tmem, a + 6, a_hi, b + 6, idesc, 1u);
+    }
+}
+
+template <int MODE, int KH_, int KW_, bool TF32, bool SPLIT>
 __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full, uint64_t* empty, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, uint32_t a_lo0, uint32_t bres_lo,
                                               uint32_t stage16, int k_iters) {
@@ -519,7 +554,7 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
     const uint32_t b_step = uint32_t(n_chunk * 8);                  // one [n_chunk x 64] weight slice in 16-byte units
     const uint32_t a16 = uint32_t(p.a_bytes >> 4);
     const int umma_k = p.kb_elems / 4;   // K elements per MMA (32 bytes): 16 halves or 8 floats
-    const int ks_last = min(4, (p.cin - (num_kb - 1) * p.kb_elems + umma_k - 1) / umma_k);   // all-zero K tail skipped
+    const int ks_last = SPLIT ? 4 : min(4, (p.cin - (num_kb - 1) * p.kb_elems + umma_k - 1) / umma_k);   // all-zero K tail skipped
     // strides between the weight slices of consecutive taps
     const uint32_t b_ky_step = resident ? uint32_t(KW * num_kb) * b_step : b_step;     // MODE 1
     const uint32_t b_tap_step = resident ? uint32_t(num_kb) * b_step : b_step;         // MODE 2
@@ -543,19 +578,13 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
             const uint32_t b_first = resident ? b_it : a_lo + a16;
             if (elect_one()) {
                 if constexpr (MODE == 0) {
-                    umma_words<TF32>(d_tmem, a_lo, kDescHi, b_first, idesc, it != 0 ? 1u : 0u);
-                    if (ks > 1) umma_words<TF32>(d_tmem, a_lo + 2, kDescHi, b_first + 2, idesc, 1u);
-                    if (ks > 2) umma_words<TF32>(d_tmem, a_lo + 4, kDescHi, b_first + 4, idesc, 1u);
-                    if (ks > 3) umma_words<TF32>(d_tmem, a_lo + 6, kDescHi, b_first + 6, idesc, 1u);
+                    umma_kblock<TF32, SPLIT>(d_tmem, a_lo, kDescHi, b_first, idesc, it != 0 ? 1u : 0u, ks);
                 } else if constexpr (MODE == 1) {
 #pragma unroll
                     for (int ky = 0; ky < KH; ky++) {
                         const uint32_t a_t = a_lo + uint32_t(ky * 128);           // next image row of the box: 16 px * 128 B
                         const uint32_t b_t = b_first + uint32_t(ky) * b_ky_step;
-                        umma_words<TF32>(d_tmem, a_t, kDescHi, b_t, idesc, (it | ky) != 0 ? 1u : 0u);
-                        if (ks > 1) umma_words<TF32>(d_tmem, a_t + 2, kDescHi, b_t + 2, idesc, 1u);
-                        if (ks > 2) umma_words<TF32>(d_tmem, a_t + 4, kDescHi, b_t + 4, idesc, 1u);
-                        if (ks > 3) umma_words<TF32>(d_tmem, a_t + 6, kDescHi, b_t + 6, idesc, 1u);
+                        umma_kblock<TF32, SPLIT>(d_tmem, a_t, kDescHi, b_t, idesc, (it | ky) != 0 ? 1u : 0u, ks);
                     }
                 } else {
 #pragma unroll
@@ -564,10 +593,7 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
                         for (int kx = 0; kx < KW; kx++) {
                             const uint32_t a_t = a_lo + (uint32_t(ky) * bw + uint32_t(kx)) * 8u;   // pixel rows of 128 B
                             const uint32_t b_t = b_first + uint32_t(ky * KW + kx) * b_tap_step;
-                            umma_words<TF32>(d_tmem, a_t, halo_hi, b_t, idesc, (it | ky | kx) != 0 ? 1u : 0u);
-                            if (ks > 1) umma_words<TF32>(d_tmem, a_t + 2, halo_hi, b_t + 2, idesc, 1u);
-                            if (ks > 2) umma_words<TF32>(d_tmem, a_t + 4, halo_hi, b_t + 4, idesc, 1u);
-                            if (ks > 3) umma_words<TF32>(d_tmem, a_t + 6, halo_hi, b_t + 6, idesc, 1u);
+                            umma_kblock<TF32, SPLIT>(d_tmem, a_t, halo_hi, b_t, idesc, (it | ky | kx) != 0 ? 1u : 0u, ks);
                         }
                 }
                 umma_commit(&empty[stage]);                            // smem slot is free once these MMAs have read it
@@ -586,7 +612,10 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+// SPLIT: the fp32-activation / 3-term fp16 product variant (p.split; 4 extra operand-transform warps).  A separate
+// instantiation so that the plain fp16 / tf32 kernel keeps its 320-thread register budget.
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kThreads : kThreadsBase, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -598,13 +627,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.halo ? p.kh * p.kw : p.rowbox ? p.kh : 1);
     const int stage_bytes = p.a_bytes + b_bytes;
     uint8_t* bres = smem + size_t(p.stages) * stage_bytes;          // resident weights: [tap][k-block][n_chunk x 64]
-    uint8_t* sout = bres + p.b_total;                               // kOutBufs staging tiles for the TMA stores
-    uint64_t* full = reinterpret_cast<uint64_t*>(sout + kOutBufs * kOutBufBytes);
+    uint8_t* sout = bres + p.b_total;                               // p.out_bufs staging tiles for the TMA stores
+    uint64_t* full = reinterpret_cast<uint64_t*>(sout + p.out_bufs * kOutBufBytes);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
     uint64_t* tmem_empty = tmem_full + kMaxAccStages;
     uint64_t* b_full = tmem_empty + kMaxAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+    uint64_t* xf = b_full + 1;                                      // split mode: operand rows of a stage are transformed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf + p.stages);
     float* sparam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kBarRegion);
     const float *pb = p.bias, *ps = p.post_scale, *pt = p.post_shift;
     if (p.param_smem) {
@@ -627,6 +657,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int s = 0; s < p.stages; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&xf[s], kXfWarps);
         }
         for (int s = 0; s < p.acc_stages; s++) {
             mbar_init(&tmem_full[s], 1);
@@ -652,7 +683,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_expect_tx(b_full, uint32_t(p.b_total));
         for (int tp = 0; tp < taps; tp++)
             for (int kb = 0; kb < p.num_kb; kb++)
-                tma_load_2d(bres + size_t(tp * p.num_kb + kb) * p.n_chunk * 128, &map_b, b_full, tp * p.k_pad + kb * p.kb_elems, 0);
+                tma_load_2d(bres + size_t(tp * p.num_kb + kb) * p.n_chunk * 128, &map_b, b_full, tp * p.k_pad + kb * p.kbb, 0);
     }
     pdl_wait();
     pdl_trigger();
@@ -680,13 +711,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (p.halo) {
                         tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 - p.pw, y0 - p.ph, img);
                         for (int tp = 0; tp < taps && !p.b_resident; tp++)
-                            tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * p.kb_elems,
+                            tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * p.kbb,
                                         n_idx * p.n_chunk);
                     } else if (p.rowbox) {
                         tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 + tap - p.pw, y0 - p.ph, img);
                         for (int ky = 0; ky < p.kh && !p.b_resident; ky++)
                             tma_load_2d(a_dst + p.a_bytes + ky * p.n_chunk * 128, &map_b, &full[stage],
-                                        (ky * p.kw + tap) * p.k_pad + kb * p.kb_elems, n_idx * p.n_chunk);
+                                        (ky * p.kw + tap) * p.k_pad + kb * p.kbb, n_idx * p.n_chunk);
                     } else {
                         if (p.spatial) {
                             const int ky = tap / p.kw, kx = tap - ky * p.kw;
@@ -695,7 +726,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             tma_load_2d(a_dst, &map_a, &full[stage], kb * p.kb_elems, m_tile * BLOCK_M);
                         }
                         if (!p.b_resident)
-                            tma_load_2d(a_dst + p.a_bytes, &map_b, &full[stage], tap * p.k_pad + kb * p.kb_elems, n_idx * p.n_chunk);
+                            tma_load_2d(a_dst + p.a_bytes, &map_b, &full[stage], tap * p.k_pad + kb * p.kbb, n_idx * p.n_chunk);
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -711,8 +742,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t stage16 = uint32_t(stage_bytes >> 4);
 #define VSE_MMA(M, A, B)                                                                                                      \
     do {                                                                                                                      \
-        if (p.tf32) mma_warp_loop<M, A, B, true>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);  \
-        else mma_warp_loop<M, A, B, false>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);       \
+        if constexpr (SPLIT) mma_warp_loop<M, A, B, false, true>(p, xf, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);   \
+        else if (p.tf32) mma_warp_loop<M, A, B, true, false>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);  \
+        else mma_warp_loop<M, A, B, false, false>(p, full, empty, tmem_full, tmem_empty, tmem_base, a_lo0, bres_lo, stage16, k_iters);       \
     } while (0)
         if (p.halo) {
             if (p.kh == 3 && p.kw == 3) VSE_MMA(2, 3, 3);
@@ -724,6 +756,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             VSE_MMA(0, 1, 1);
         }
 #undef VSE_MMA
+    } else if (SPLIT && warp >= 2 + kEpiWarps) {
+        // ---------------- split mode: operand transform, warps 10..13 ----------------
+        // A stage arrives as fp32 rows of 32 channels (128 bytes, 128B-swizzled by TMA).  Each thread owns whole rows: it reads
+        // the row's eight 16-byte chunks, splits every value into fp16 hi = rn(x) and lo = rn(x - hi), and writes the row back
+        // in place as [hi(32) | lo(32)] in the same swizzle — a K-major fp16 operand row of 64 columns for kind::f16 MMAs.
+        // 16-byte accesses of 8 consecutive rows cover all 32 banks (the swizzle XOR), so the pass is conflict free.
+        // The tensor core flushes fp16 SUBNORMAL inputs to zero (measured: without scaling the products are only good to
+        // 2^-12, exactly what losing every lo < 2^-14 predicts), so both operands are scaled by powers of two first: the
+        // activations by p.a_scale, the weights per layer so that max |w| sits just below 2^14 (tc_pack_weights); the
+        // epilogue multiplies the accumulator by the exact inverse.
+        const int xt = threadIdx.x - 32 * (2 + kEpiWarps);
+        const int rows = p.a_tx >> 7;
+        const float asc = p.a_scale;
+        int stage = 0;
+        uint32_t phase = 0;
+        const long long n_it = (long long)((total_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x)) * k_iters;
+        for (long long it = 0; it < n_it; it++) {
+            mbar_wait(&full[stage], phase);
+            const uint32_t base = smem_u32(smem + size_t(stage) * stage_bytes);
+            for (int r = xt; r < rows; r += 32 * kXfWarps) {
+                const uint32_t row = base + uint32_t(r) * 128u, sw = uint32_t(r & 7);
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
+                                 : "r"(row + ((uint32_t(q) ^ sw) << 4)));
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const float sx = v[q].x * asc, sy = v[q].y * asc, sz = v[q].z * asc, sw4 = v[q].w * asc;
+                    const __half2 h0 = __floats2half2_rn(sx, sy), h1 = __floats2half2_rn(sz, sw4);
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                    const __half2 l0 = __floats2half2_rn(sx - f0.x, sy - f0.y), l1 = __floats2half2_rn(sz - f1.x, sw4 - f1.y);
+                    hi[2 * q] = *reinterpret_cast<const uint32_t*>(&h0); hi[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                    lo[2 * q] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    st_shared_16(row + ((uint32_t(q) ^ sw) << 4), make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]));
+                    st_shared_16(row + ((uint32_t(q + 4) ^ sw) << 4), make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]));
+                }
+            }
+            fence_proxy_async();                                      // generic-proxy writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xf[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
     } else {
         // ---------------- epilogue: warps 2..9 ----------------
         const int q = warp & 3, half = (warp - 2) >> 2;
@@ -745,9 +824,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 
-TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, bool tf32) {
+// split mode, layers without a calibrated input range (vse_set_conv_input_ranges): activations are multiplied by
+// 2^VSE_SPLIT_ASHIFT (default 2^2) before the fp16 split, so that the lo halves of everything above 2^-14 * 2^11 / 2^2 = 2^-5
+// stay normal fp16 numbers; the price is the range: |x| must stay below 65504 / 2^2 (violations turn into non-finite
+// outputs, which the DB post-process / CTC decode report)
+float tc_split_activation_scale() {
+    static const float s = [] {
+        const char* e = getenv("VSE_SPLIT_ASHIFT");
+        int sh = e ? atoi(e) : 2;
+        sh = std::max(0, std::min(12, sh));
+        return std::ldexp(1.f, sh);
+    }();
+    return s;
+}
+
+TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, int mode) {
+    const bool tf32 = mode == TC_TF32;
     TcWeights t;
     t.tf32 = tf32 ? 1 : 0;
+    if (mode == TC_SPLIT) {
+        // fp32 weights as fp16 hi = rn(w) and lo = rn(w - hi); per 32 input channels one 128-byte row [hi(32) | lo(32)]
+        t.split = 1;
+        const int n_mma = round_up_i(cout, 16);
+        t.n_chunks = (n_mma + 255) / 256;
+        t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, t.n_chunks > 1 ? 64 : 16);
+        const int num_kb = (cin + 31) / 32;
+        t.k_pad = num_kb * 64;                     // columns (halves) per tap
+        t.taps = taps;
+        const size_t rows = size_t(t.n_chunks) * t.n_chunk, cols = size_t(taps) * t.k_pad;
+        t.b.assign(rows * cols, 0);
+        // power-of-two weight scale: max |w| * scale in [2^13, 2^14) keeps hi AND lo = w - hi of every weight that matters in
+        // the fp16 normal range (the tensor core flushes subnormal inputs)
+        float wmax = 0.f;
+        for (size_t i = 0; i < size_t(cout) * taps * cin; i++) wmax = std::max(wmax, std::fabs(w[i]));
+        int e = 0;
+        if (wmax > 0.f) {
+            std::frexp(wmax, &e);               // wmax = m * 2^e, m in [0.5, 1)
+            e = 14 - e;                         // wmax * 2^e in [2^13, 2^14)
+        }
+        e = std::max(-24, std::min(24, e));
+        t.w_scale = std::ldexp(1.f, e);
+        for (int co = 0; co < cout; co++)
+            for (int tp = 0; tp < taps; tp++)
+                for (int ci = 0; ci < cin; ci++) {
+                    const float f = w[(size_t(co) * taps + tp) * cin + ci] * t.w_scale;
+                    const __half h = __float2half_rn(f);
+                    const __half l = __float2half_rn(f - __half2float(h));
+                    const size_t at = size_t(co) * cols + size_t(tp) * t.k_pad + size_t(ci / 32) * 64 + (ci % 32);
+                    std::memcpy(&t.b[at], &h, 2);
+                    std::memcpy(&t.b[at + 32], &l, 2);
+                }
+        return t;
+    }
     const int kb = tf32 ? 32 : BLOCK_K;            // elements per 128-byte K row
     const int n_mma = round_up_i(cout, 16);
     t.n_chunks = (n_mma + 255) / 256;
@@ -825,7 +953,8 @@ static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t
 std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, bool flat,
                           int64_t pixels, int n_img, int H, int W, int kh, int kw, int ph, int pw, bool allow_rowbox, bool allow_halo) {
     t.valid = false;
-    if ((reinterpret_cast<uintptr_t>(in) & 15) || (!w.tf32 && (in_cs & 7))) return "activation view not 16-byte aligned";
+    const bool a32 = w.tf32 || w.split;          // fp32 activations
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (!a32 && (in_cs & 7))) return "activation view not 16-byte aligned";
     if (pixels <= 0) return "empty";
     t.kh = kh; t.kw = kw; t.ph = ph; t.pw = pw;
     t.k_pad = w.k_pad;
@@ -833,15 +962,18 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
     t.rowbox = 0;
     t.halo = 0;
     t.tf32 = w.tf32;
-    const int es = w.tf32 ? 4 : 2;               // activation / weight element size
-    const cuuint32_t kbe = cuuint32_t(128 / es);   // elements per 128-byte K row (64 halves or 32 floats)
-    if (w.tf32 && (in_cs & 3)) return "fp32 activation view not 16-byte aligned";
+    t.split = w.split;
+    t.w_scale = w.split ? w.w_scale : 1.f;
+    const int es = a32 ? 4 : 2;                  // activation element size
+    const int es_b = w.tf32 ? 4 : 2;             // weight element size (split: fp16 hi | lo)
+    const cuuint32_t kbe = cuuint32_t(128 / es);   // activation elements per 128-byte K row (64 halves or 32 floats)
+    if (a32 && (in_cs & 3)) return "fp32 activation view not 16-byte aligned";
     t.num_kb = (cin + int(kbe) - 1) / int(kbe);
     t.n_chunk = w.n_chunk;
     t.n_chunks = w.n_chunks;
     // weights resident in shared memory when the whole (single-chunk) matrix is small: tiles then stream activations only
     const int b_all = kh * kw * t.num_kb * w.n_chunk * 128;
-    t.b_resident = (w.n_chunks == 1 && b_all <= kBResidentMax) ? 1 : 0;
+    t.b_resident = (w.n_chunks == 1 && b_all <= (w.split ? kBResidentMaxSplit : kBResidentMax)) ? 1 : 0;
     std::string err;
     if (flat) {
         t.spatial = 0;
@@ -850,15 +982,16 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         cuuint64_t dims[2] = {cuuint64_t(cin), cuuint64_t(pixels)};
         cuuint64_t strides[1] = {cuuint64_t(in_cs) * es};
         cuuint32_t box[2] = {kbe, BLOCK_M};
-        err = encode(&t.map_a, const_cast<void*>(in), 2, dims, strides, box, w.tf32);
+        err = encode(&t.map_a, const_cast<void*>(in), 2, dims, strides, box, a32);
     } else {
         t.spatial = 1;
         t.n_img = n_img; t.H = H; t.W = W;
         // halo tiles (16 rows x 8 columns) for kernels up to 5x5: needs >= 3 stages of one box (+ the taps' weight slices)
         const int h_box = (16 + kh - 1) * (8 + kw - 1) * 128;
+        const int slack = w.split ? 4096 : 16384;   // barriers, epilogue constants, alignment
         const int h_stage = round_up_i(h_box, 1024) + (t.b_resident ? 0 : kh * kw * w.n_chunk * 128);
         t.halo = (allow_halo && kh > 1 && kh <= 5 && kw <= 5 && kw > 1 &&
-                  3 * h_stage + (t.b_resident ? b_all : 0) <= kMaxSmem - 16384 - kOutBufs * kOutBufBytes) ? 1 : 0;
+                  3 * h_stage + (t.b_resident ? b_all : 0) <= kMaxSmem - slack - (w.split ? 2 : kOutBufs) * kOutBufBytes) ? 1 : 0;
         t.tiles_x = t.halo ? (W + 7) / 8 : (W + 15) / 16;
         t.tiles_y = t.halo ? (H + 15) / 16 : (H + 7) / 8;
         t.num_m_tiles = n_img * t.tiles_x * t.tiles_y;
@@ -868,15 +1001,15 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         // traffic for the activations.  Needs >= 3 pipeline stages of (box + kh weight slices) in shared memory.
         const int a_box = (8 + kh - 1) * 16 * 128;
         const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + kh * w.n_chunk * 128);
-        t.rowbox = (!t.halo && allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - 16384 - kOutBufs * kOutBufBytes) ? 1 : 0;
+        t.rowbox = (!t.halo && allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - slack - (w.split ? 2 : kOutBufs) * kOutBufBytes) ? 1 : 0;
         cuuint32_t box[4] = {kbe, cuuint32_t(t.halo ? 8 + kw - 1 : 16), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + kh - 1 : 8), 1};
-        err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box, w.tf32);
+        err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box, a32);
     }
     if (!err.empty()) return err;
     {
         cuuint64_t dims[2] = {cuuint64_t(w.taps) * w.k_pad, cuuint64_t(w.n_chunks) * w.n_chunk};
-        cuuint64_t strides[1] = {cuuint64_t(w.taps) * w.k_pad * es};
-        cuuint32_t box[2] = {kbe, cuuint32_t(w.n_chunk)};
+        cuuint64_t strides[1] = {cuuint64_t(w.taps) * w.k_pad * es_b};
+        cuuint32_t box[2] = {cuuint32_t(128 / es_b), cuuint32_t(w.n_chunk)};
         err = encode(&t.map_b, const_cast<void*>(wdev), 2, dims, strides, box, w.tf32);
         if (!err.empty()) return err;
     }
@@ -888,25 +1021,26 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
 static std::string tc_output_map(TcConv& t) {
     if (t.map_o_ptr == t.out && t.map_o_cs == t.out_cs && t.map_o_n == t.n_store) return "";
     std::string err;
-    const int es = t.tf32 ? 4 : 2;
+    const int es = (t.tf32 || t.split) ? 4 : 2;
     const cuuint32_t cols = cuuint32_t(128 / es);   // one staging row = 64 fp16 or 32 fp32 columns
     if (t.spatial) {
         cuuint64_t dims[4] = {cuuint64_t(t.n_store), cuuint64_t(t.W), cuuint64_t(t.H), cuuint64_t(t.n_img)};
         cuuint64_t strides[3] = {cuuint64_t(t.out_cs) * es, cuuint64_t(t.W) * t.out_cs * es, cuuint64_t(t.H) * t.W * t.out_cs * es};
         cuuint32_t box[4] = {cols, cuuint32_t(t.halo ? 8 : 16), cuuint32_t(t.halo ? 16 : 8), 1};
-        err = encode(&t.map_o, t.out, 4, dims, strides, box, t.tf32);
+        err = encode(&t.map_o, t.out, 4, dims, strides, box, es == 4);
     } else {
         cuuint64_t dims[2] = {cuuint64_t(t.n_store), cuuint64_t(t.M)};
         cuuint64_t strides[1] = {cuuint64_t(t.out_cs) * es};
         cuuint32_t box[2] = {cols, BLOCK_M};
-        err = encode(&t.map_o, t.out, 2, dims, strides, box, t.tf32);
+        err = encode(&t.map_o, t.out, 2, dims, strides, box, es == 4);
     }
     if (err.empty()) { t.map_o_ptr = t.out; t.map_o_cs = t.out_cs; t.map_o_n = t.n_store; }
     return err;
 }
 
 std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
-    if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (t.tf32 ? 3 : 7))) return "output view not 16-byte aligned";
+    const bool of32 = t.tf32 || t.split;
+    if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (of32 ? 3 : 7))) return "output view not 16-byte aligned";
     {
         std::string err = tc_output_map(t);
         if (!err.empty()) return err;
@@ -917,7 +1051,9 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = t.num_m_tiles;
     p.cin = t.cin;
     p.tf32 = t.tf32;
-    p.kb_elems = t.tf32 ? 32 : BLOCK_K;
+    p.split = t.split;
+    p.kb_elems = of32 ? 32 : BLOCK_K;              // activation elements per k-block
+    p.kbb = t.split ? 64 : p.kb_elems;             // weight columns per k-block
     p.rowbox = t.rowbox;
     p.halo = t.halo;
     p.a_tx = t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh - 1) * 16 * 128 : A_BYTES;
@@ -928,7 +1064,14 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     p.b_resident = t.b_resident;
     p.b_total = t.b_resident ? t.kh * t.kw * t.num_kb * t.n_chunk * 128 : 0;
     const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.halo ? t.kh * t.kw : t.rowbox ? t.kh : 1));
-    const int budget = kMaxSmem - 1024 - kBarRegion - param_bytes - p.b_total - kOutBufs * kOutBufBytes;
+    // staging ring of the TMA stores: 4 tiles; split mode (operand stages and weights are twice the bytes) gives tiles back
+    // to the operand pipeline until it holds 3 stages
+    p.out_bufs = kOutBufs;
+    int budget = kMaxSmem - 1024 - kBarRegion - param_bytes - p.b_total - p.out_bufs * kOutBufBytes;
+    while (t.split && p.out_bufs > 2 && budget / stage_bytes < 3) {
+        p.out_bufs--;
+        budget += kOutBufBytes;
+    }
     p.stages = std::max(2, std::min(8, budget / stage_bytes));
     // TMEM accumulator ring: the MMA warp runs up to acc_stages tiles ahead of the epilogue (hides the commit -> wait ->
     // tcgen05.ld -> arrive round trip, which dominates layers with one k-iteration per tile)
@@ -941,17 +1084,22 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     p.res = t.epi.res; p.res_cs = t.epi.res_cs; p.act = t.epi.act; p.act2 = t.epi.act2;
     p.hs_slope = t.epi.hs_slope; p.hs_offset = t.epi.hs_offset;
     p.gate = t.epi.gate; p.gate_c = t.epi.gate_c; p.gate_rows = std::max(t.epi.gate_rows, 1);
-    const size_t smem = size_t(p.stages) * stage_bytes + p.b_total + kOutBufs * kOutBufBytes + 1024 + kBarRegion + param_bytes;
+    p.a_scale = t.split ? (t.a_scale > 0.f ? t.a_scale : tc_split_activation_scale()) : 1.f;
+    p.acc_scale = t.split ? 1.f / (p.a_scale * t.w_scale) : 1.f;
+    const size_t smem = size_t(p.stages) * stage_bytes + p.b_total + p.out_bufs * kOutBufBytes + 1024 + kBarRegion + param_bytes;
+    if (smem > size_t(kMaxSmem)) return "operand stages do not fit shared memory";
     static bool configured[64] = {};   // per device: the attribute belongs to the device's copy of the kernel
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int total = t.num_m_tiles * t.n_chunks;
     const int grid = std::max(1, std::min(total, sm_count));
-    pdl_launch(conv_tc_kernel, grid, kThreads, smem, st, t.map_a, t.map_b, t.map_o, p);
+    if (t.split) pdl_launch(conv_tc_kernel<true>, grid, kThreads, smem, st, t.map_a, t.map_b, t.map_o, p);
+    else pdl_launch(conv_tc_kernel<false>, grid, kThreadsBase, smem, st, t.map_a, t.map_b, t.map_o, p);
     return "";
 }
 

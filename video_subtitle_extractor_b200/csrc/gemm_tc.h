@@ -18,17 +18,22 @@ struct TcWeights {          // built once per plan step (host), uploaded as fp16
     int k_pad = 0;          // per-tap K extent in the B matrix (multiple of 64)
     int taps = 1;
     int tf32 = 0;           // 1: fp32 elements (tcgen05 kind::tf32), k_pad a multiple of 32; 0: fp16, multiple of 64
+    int split = 0;          // 1: fp16 hi | lo halves of fp32 weights, 64 columns per 32 input channels (see gemm_tc.cu, "split" mode)
+    float w_scale = 1.f;    // split: power of two the weights were multiplied by before the split
     std::vector<uint16_t> b;  // raw 16-bit words: fp16 bits (or 2 words per fp32), [n_chunks * n_chunk][taps * k_pad], K-major, zero padded
 };
 
 // cout / cin: real channel counts; weights fp32 [cout][kh*kw][cin]
-TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, bool tf32 = false);
+enum TcMode { TC_F16 = 0, TC_TF32 = 1, TC_SPLIT = 2 };
+TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, int mode = TC_F16);
 
 // Pixel-packed 1x1 conv: `pack` consecutive pixels (channel stride in_cs, pack * in_cs == 64) form ONE GEMM row of K = 64
 // and the weights become block-diagonal [pack * out_cs][64]: row g*out_cs + co, column g*in_cs + ci = w[co][ci].  The
 // activation rows are then 128 bytes wide (TMA moves narrow 32/64-byte pixel rows at a fraction of its line rate) and the
 // `pack` output pixels of a row are contiguous in memory.
 TcWeights tc_pack_weights_pixelpacked(const float* w, int cout, int cin, int in_cs, int out_cs, int pack);
+
+float tc_split_activation_scale();
 
 struct TcConv {
     CUtensorMap map_a;      // activations (2-D flat for 1x1, 4-D [C][W][H][N] for KxK)
@@ -43,6 +48,9 @@ struct TcConv {
     int cin = 0;            // real input channels (the MMA loop skips the all-zero tail of the last K block)
     int rowbox = 0;         // KxK: A boxes span 8 + kh - 1 image rows and serve all vertical taps (see gemm_tc.cu)
     int tf32 = 0;           // fp32 activations / weights through kind::tf32 MMAs, fp32 output
+    int split = 0;          // fp32 activations split in place into fp16 hi | lo, three kind::f16 MMAs per product, fp32 output
+    float w_scale = 1.f;
+    float a_scale = 0.f;    // split: power of two for the operand rows (0 = the default of tc_split_activation_scale())
     int pack = 0;           // >0: pixel-packed flat conv (rows of `pack` pixels)
     int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
     int halo = 0;           // KxK: one (16 + kh - 1) x (8 + kw - 1) box per k-block serves every tap (see gemm_tc.cu)

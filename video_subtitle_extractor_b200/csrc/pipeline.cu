@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 #include "dbpost_core.cuh"
 #include "pdl.cuh"
@@ -29,6 +30,10 @@ struct Engine::Pipeline {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t fdone[2] = {nullptr, nullptr};
     std::vector<Pending> pending;             // oldest first, at most 2
+    // vse_prefetch may be called from a producer thread while vse_run computes on the consumer thread: `mu` guards the
+    // pending list and the choice of staging buffer; `busy` is the buffer the running batch reads (never handed out)
+    std::mutex mu;
+    int busy = -1;
     DevBuf labels, slot_of, n_comp, roots, bbox, order, cand, status, n_boxes, quads, scores, blk_fg;
     DevBuf cubic_tab, crop_jobs, crop_buf, rec_jobs, rec_in;
     DevBuf ctc_meta, ctc_ids, ctc_len, ctc_score;
@@ -141,7 +146,9 @@ void Engine::db_post_device(const float* prob, const std::vector<DetFrame>& fram
     }
     if (max_rh > 2048) throw InvalidArg{"detection map taller than 2048 rows"};
     if (max_rw > 32 * 1023 || n > 2047) throw InvalidArg{"detection batch beyond the post-process limits (2047 frames, 32736 columns)"};
-    const int mb = cfg.max_boxes_per_frame, mc = std::min(std::max(cfg.det_max_candidates, 1), kSlotCap);
+    const int mc = std::min(std::max(cfg.det_max_candidates, 1), kSlotCap);
+    cfg.max_boxes_per_frame = std::min(std::max(cfg.max_boxes_per_frame, 1), mc);   // upstream keeps at most max_candidates boxes
+    int mb = cfg.max_boxes_per_frame;
     P->labels.reserve(total * sizeof(int));
     P->slot_of.reserve(total * sizeof(int));
     P->blk_fg.reserve((size_t(n) * ((max_rh + 7) / 8) * ((max_rw + 31) / 32) + 4) * sizeof(int));
@@ -161,23 +168,39 @@ void Engine::db_post_device(const float* prob, const std::vector<DetFrame>& fram
     DbParams dp{cfg.det_thresh, cfg.det_box_thresh, cfg.det_unclip_ratio, mc, mb, reading_order ? 1 : 0};
     launch_db_postprocess(prob, P->det_frames.as<DetFrame>(), frames.data(), n, max_rh, max_rw, dp, make_ws(P), stream, &launches);
     VSE_CUDA(cudaGetLastError());
-    const size_t bytes = size_t(n) * (2 * sizeof(int) + mb * sizeof(float) * 9);
-    P->h_out.reserve(bytes);
-    char* h = P->h_out.as<char>();
-    VSE_CUDA(cudaMemcpyAsync(h, P->n_boxes.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    VSE_CUDA(cudaMemcpyAsync(h + n * sizeof(int), P->status.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    VSE_CUDA(cudaMemcpyAsync(h + 2 * n * sizeof(int), P->scores.p, size_t(n) * mb * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    VSE_CUDA(cudaMemcpyAsync(h + 2 * n * sizeof(int) + size_t(n) * mb * sizeof(float), P->quads.p, size_t(n) * mb * 8 * sizeof(float),
-                             cudaMemcpyDeviceToHost, stream));
-    VSE_CUDA(cudaStreamSynchronize(stream));
-    const int* status = reinterpret_cast<const int*>(h + n * sizeof(int));
+    char* h = nullptr;
+    const int* status = nullptr;
+    for (;;) {
+        const size_t bytes = size_t(n) * (2 * sizeof(int) + mb * sizeof(float) * 9);
+        P->h_out.reserve(bytes);
+        h = P->h_out.as<char>();
+        VSE_CUDA(cudaMemcpyAsync(h, P->n_boxes.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        VSE_CUDA(cudaMemcpyAsync(h + n * sizeof(int), P->status.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        VSE_CUDA(cudaMemcpyAsync(h + 2 * n * sizeof(int), P->scores.p, size_t(n) * mb * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        VSE_CUDA(cudaMemcpyAsync(h + 2 * n * sizeof(int) + size_t(n) * mb * sizeof(float), P->quads.p, size_t(n) * mb * 8 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, stream));
+        VSE_CUDA(cudaStreamSynchronize(stream));
+        status = reinterpret_cast<const int*>(h + n * sizeof(int));
+        bool overflow = false;
+        for (int i = 0; i < n; i++) overflow |= (status[i] & 2) != 0;
+        if (!overflow || mb >= mc) break;
+        // a frame holds more boxes than the per-frame rows (dense text, credits): the candidates are still on the device,
+        // so only the compaction is repeated with more rows — up to max_candidates, which is all upstream ever keeps
+        mb = std::min(mc, mb * 4);
+        cfg.max_boxes_per_frame = mb;
+        P->quads.reserve(size_t(n) * mb * 8 * sizeof(float));
+        P->scores.reserve(size_t(n) * mb * sizeof(float));
+        dp.max_boxes = mb;
+        launch_db_compact(n, dp, make_ws(P), stream, &launches);
+        VSE_CUDA(cudaGetLastError());
+    }
     for (int i = 0; i < n; i++) {
         if (status[i] & 4)
             throw StateError{"frame " + std::to_string(i) + ": the detection map holds non-finite values — this model's activations "
                              "exceed the fp16 range (e.g. V4/ch_det: LK-PAN outputs reach 1.5e5); create the engine with "
                              "VSE_FLAG_DET_FP32 (or VSE_PRECISION_FP32) for it"};
         if (status[i] & 1) throw InvalidArg{"frame " + std::to_string(i) + ": more than 4096 connected components in the detection map"};
-        if (status[i] & 2) throw CapacityError{"frame " + std::to_string(i) + ": more boxes than max_boxes_per_frame"};
+        if (status[i] & 2) throw CapacityError{"frame " + std::to_string(i) + ": more boxes than max_boxes_per_frame"};   // unreachable: rows == max_candidates
     }
 }
 
@@ -236,12 +259,23 @@ void Engine::prefetch_frames(const uint8_t* const* frames, const int32_t* h, con
     Pipeline* P = pipe_;
     std::vector<int> fstride(n);
     frame_strides(frames, h, w, stride, n, fstride);
-    if (P->pending.size() >= 2) {                  // no free buffer: the oldest unused prefetch gives way
+    std::lock_guard<std::mutex> lock(P->mu);
+    // buffers a prefetch may use: not the one the running batch reads; an unused older prefetch gives way
+    auto holds = [&](int b) { for (auto& q : P->pending) if (q.buf == b) return true; return false; };
+    int buf = -1;
+    for (int b = 0; b < 2 && buf < 0; b++)
+        if (b != P->busy && !holds(b)) buf = b;
+    if (buf < 0) {
         VSE_CUDA(cudaStreamSynchronize(P->copy_stream));
-        P->pending.erase(P->pending.begin());
+        for (size_t q = 0; q < P->pending.size() && buf < 0; q++)
+            if (P->pending[q].buf != P->busy) {
+                buf = P->pending[q].buf;
+                P->pending.erase(P->pending.begin() + q);
+            }
+        if (buf < 0) throw StateError{"no staging buffer free for vse_prefetch"};
     }
     Pipeline::Pending pe;
-    pe.buf = P->pending.empty() ? 0 : 1 - P->pending[0].buf;
+    pe.buf = buf;
     pe.dev.assign(n, nullptr);
     // growing the buffer frees the old allocation (implicit device sync); the run that last used it has returned
     stage_frames(frames, h, w, fstride, n, P->fbuf[pe.buf], P->copy_stream, pe.dev);
@@ -264,16 +298,20 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
     if (mem_kind < VSE_MEM_HOST || mem_kind > VSE_MEM_DEVICE) throw InvalidArg{"bad mem_kind"};
     ensure_pipeline();
     Pipeline* P = pipe_;
-    const int mb = cfg.max_boxes_per_frame;
     VSE_CUDA(cudaEventRecord(P->ev[0], stream));
 
     // 1. frames -> device (already there when vse_prefetch staged exactly this batch)
     std::vector<const uint8_t*> fdev(n);
     std::vector<int> fstride(n);
     frame_strides(frames, h, w, stride, n, fstride);
+    struct BusyGuard {      // the staging buffer of this batch is released on every way out of the call
+        Pipeline* P;
+        ~BusyGuard() { std::lock_guard<std::mutex> lock(P->mu); P->busy = -1; }
+    } busy_guard{P};
     if (mem_kind == VSE_MEM_DEVICE) {
         for (int i = 0; i < n; i++) fdev[i] = frames[i];
     } else {
+        std::lock_guard<std::mutex> lock(P->mu);
         int hit = -1;
         for (size_t q = 0; q < P->pending.size() && hit < 0; q++) {
             const Pipeline::Pending& pe = P->pending[q];
@@ -285,6 +323,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         if (hit >= 0) {
             VSE_CUDA(cudaStreamWaitEvent(stream, P->fdone[P->pending[hit].buf], 0));
             fdev = P->pending[hit].dev;
+            P->busy = P->pending[hit].buf;
             P->pending.erase(P->pending.begin() + hit);
         } else {
             int buf = 0;
@@ -294,6 +333,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
             } else if (P->pending.size() == 1) {
                 buf = 1 - P->pending[0].buf;
             }
+            P->busy = buf;
             stage_frames(frames, h, w, fstride, n, P->fbuf[buf], stream, fdev);
         }
     }
@@ -338,6 +378,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
     std::vector<DetFrame> dfr(n);
     for (int i = 0; i < n; i++) dfr[i] = DetFrame{geo->tab[i].off, geo->tab[i].h, geo->tab[i].w, h[i], w[i]};
     db_post_device(prob, dfr, !det_only);
+    const int mb = cfg.max_boxes_per_frame;      // (db_post_device grows it when a frame holds more boxes)
     VSE_CUDA(cudaEventRecord(P->ev[4], stream));
     const char* hb = P->h_out.as<char>();
     const int* nb = reinterpret_cast<const int*>(hb);
@@ -474,7 +515,8 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         pdl_launch(resize_bilinear_u8_kernel, grid, 256, 0, stream, P->rec_jobs.as<ResizeJob>(), P->rec_in.as<uint8_t>(), max_rec_pix);
         launches++;
         VSE_CUDA(cudaGetLastError());
-        VSE_CUDA(cudaStreamSynchronize(stream));  // h_in is reused by run_plan's table upload
+        // no synchronisation here: launch_upload copies its source into the kernel's parameters at launch time, so h_in
+        // (and the engine's table staging, run_plan) may be rewritten as soon as the call returns
     }
     VSE_CUDA(cudaEventRecord(P->ev[5], stream));
 
@@ -519,6 +561,9 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         const int* hlen = reinterpret_cast<const int*>(ho + ids_bytes);
         const float* hsc = reinterpret_cast<const float*>(ho + ids_bytes + nC * sizeof(int));
         for (int k = 0; k < nC; k++) {
+            if (hlen[k] < 0)
+                throw StateError{"text line " + std::to_string(k) + ": the recogniser produced non-finite class probabilities — its "
+                                 "activations exceed the fp16 range; create the engine with VSE_PRECISION_FP32 or VSE_PRECISION_TF32"};
             if (hlen[k] > out->max_text_len) throw CapacityError{"result.max_text_len too small for a line of " + std::to_string(hlen[k]) + " symbols"};
             std::memcpy(out->ids + size_t(k) * out->max_text_len, hid + size_t(k) * max_t, hlen[k] * sizeof(int));
             out->id_len[k] = hlen[k];

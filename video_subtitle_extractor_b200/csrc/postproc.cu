@@ -296,6 +296,13 @@ __global__ void __launch_bounds__(kCandThreads) db_candidates(const float* __res
     }
 }
 
+__global__ void db_clear_overflow(int* status, int n) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) status[i] &= ~2;
+}
+
 // keep valid candidates in contour order, optionally re-order like TextSystem.sorted_boxes
 __global__ void db_compact(const int* __restrict__ n_comp, const float* __restrict__ cand, DbParams p, int* n_boxes,
                            float* quads, float* scores, int* status) {
@@ -366,15 +373,26 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
     pdl_launch(db_bbox, pgrid, blk, 0, st, frames_dev, ws.labels, ws.slot_of, ws.bbox, ws.fg_count, ws.fg_list);
     pdl_launch(db_sort_components, n_frames, 256, 0, st, ws.n_comp, ws.roots, ws.order, ws.status);
     size_t smem = db_candidate_smem_bytes(max_rh);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(db_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    {   // the opt-in belongs to the current device's copy of the kernel: one high-water mark per device
+        static size_t configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+            if (cudaFuncSetAttribute(db_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
+            if (dev >= 0 && dev < 64) configured[dev] = smem;
+        }
     }
     pdl_launch(db_candidates, dim3(16, n_frames), kCandThreads, smem, st, prob, frames_dev, ws.labels, ws.n_comp, ws.roots, ws.bbox,
                                                                   ws.order, p, max_rh, ws.cand);
     pdl_launch(db_compact, n_frames, 32, 0, st, ws.n_comp, ws.cand, p, ws.n_boxes, ws.quads, ws.scores, ws.status);
     if (launches) *launches += 7;
+}
+
+// the compaction alone, with p.max_boxes rows per frame (the candidates of the last launch_db_postprocess are reused)
+void launch_db_compact(int n_frames, const DbParams& p, const DbWorkspace& ws, cudaStream_t st, int64_t* launches) {
+    pdl_launch(db_clear_overflow, (n_frames + 255) / 256, 256, 0, st, ws.status, n_frames);
+    pdl_launch(db_compact, n_frames, 32, 0, st, ws.n_comp, ws.cand, p, ws.n_boxes, ws.quads, ws.scores, ws.status);
+    if (launches) *launches += 2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -411,6 +429,9 @@ __global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict
                                                          int* __restrict__ id_len, float* __restrict__ score) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
     extern __shared__ __align__(8) unsigned char sm[];
     int* bi = reinterpret_cast<int*>(sm);
     float* bp = reinterpret_cast<float*>(bi + max_t);
@@ -422,20 +443,28 @@ __global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict
         const float* row = base + size_t(t) * C;
         float best = -FLT_MAX;
         int idx = 0x7fffffff;
+        bool nonfinite = false;
         for (int c = lane; c < C; c += 32) {
             const float v = row[c];
+            nonfinite |= !(fabsf(v) <= FLT_MAX);
             if (v > best) { best = v; idx = c; }
         }
+        if (nonfinite) bad = 1;   // NaN / Inf in the class probabilities (fp16 overflow inside the recogniser plan)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
         }
-        if (lane == 0) { bi[t] = idx; bp[t] = best; }
+        if (lane == 0) { bi[t] = idx < C ? idx : 0; bp[t] = best; }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (bad) {   // reported as id_len = -1: run_frames turns it into a StateError that names the fix
+            id_len[n] = -1;
+            score[n] = 0.f;
+            return;
+        }
         int m = 0;
         float s = 0.f;
         int prev = -1;
@@ -457,10 +486,14 @@ void launch_ctc_decode(const float* probs, int C, const int* toff, const int* tl
                        float* score, cudaStream_t st) {
     if (n <= 0) return;
     size_t smem = size_t(max_t) * 8;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaFuncSetAttribute(ctc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    if (smem > 48 * 1024) {
+        static size_t configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+            if (cudaFuncSetAttribute(ctc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
+            if (dev >= 0 && dev < 64) configured[dev] = smem;
+        }
     }
     pdl_launch(ctc_decode_kernel, n, 128, smem, st, probs, C, toff, tlen, max_t, ids, id_len, score);
 }

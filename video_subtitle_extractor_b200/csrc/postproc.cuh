@@ -47,6 +47,8 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
                            int max_rh, int max_rw, const DbParams& p, const DbWorkspace& ws, cudaStream_t st,
                            int64_t* launches);
 
+void launch_db_compact(int n_frames, const DbParams& p, const DbWorkspace& ws, cudaStream_t st, int64_t* launches);
+
 struct CropJob {
     const uint8_t* frame;   // source frame (device), BGR or BGRX rows
     int fh, fw, stride, pix;

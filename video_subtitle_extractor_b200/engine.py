@@ -17,7 +17,7 @@ _lib = None
 
 PLAN_DET, PLAN_REC = 0, 1
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
-PRECISION_FP16, PRECISION_FP32, PRECISION_TF32 = 0, 1, 2
+PRECISION_FP16, PRECISION_FP32, PRECISION_TF32, PRECISION_FP32_TC = 0, 1, 2, 3
 FLAG_NO_TENSOR_CORES = 1
 FLAG_NO_FAST_KERNELS = 2
 FLAG_NO_FUSED_HEAD, FLAG_NO_SE_FUSION, FLAG_NO_ROWBOX, FLAG_NO_FAST_DW, FLAG_NO_FAST_STEM, FLAG_NO_PIXEL_PACK = 4, 8, 16, 32, 64, 128
@@ -41,7 +41,7 @@ class VseResult(C.Structure):
 
 
 EXPORTS = ["vse_default_config", "vse_abi_version", "vse_device_count", "vse_create", "vse_destroy", "vse_last_error",
-           "vse_load_plan", "vse_run", "vse_det_only", "vse_prefetch", "vse_launch_count", "vse_tc_launch_count", "vse_debug_run_plan", "vse_debug_get_value",
+           "vse_load_plan", "vse_set_conv_input_ranges", "vse_run", "vse_det_only", "vse_prefetch", "vse_launch_count", "vse_tc_launch_count", "vse_debug_run_plan", "vse_debug_get_value",
            "vse_debug_resize_bilinear", "vse_debug_db_postprocess", "vse_debug_crop", "vse_debug_time_steps"]
 
 
@@ -68,6 +68,7 @@ def load_library(path: Optional[str] = None):
     lib.vse_last_error.argtypes = [vp]
     lib.vse_last_error.restype = C.c_char_p
     lib.vse_load_plan.argtypes = [vp, i32, vp, C.c_size_t]
+    lib.vse_set_conv_input_ranges.argtypes = [vp, i32, p_f32, i32]
     for fn in (lib.vse_run, lib.vse_det_only):
         fn.argtypes = [vp, pp_u8, p_i32, p_i32, p_i32, i32, i32, C.POINTER(VseResult)]
     lib.vse_prefetch.argtypes = [vp, pp_u8, p_i32, p_i32, p_i32, i32, i32]
@@ -84,6 +85,20 @@ def load_library(path: Optional[str] = None):
     lib.vse_debug_time_steps.argtypes = [vp, i32, i32, p_f32, C.POINTER(C.c_int64), i32]
     _lib = lib
     return lib
+
+
+def bench_mode() -> dict:
+    """Engine keyword arguments of the mode bench.py times (BASELINE configs[1]); tests/test_gpu_real_video.py holds exactly
+    this mode to the north-star bars (IoU >= 0.99 box-for-box, CER <= 1e-3) on the reference's sample videos."""
+    return dict(precision=PRECISION_FP16)
+
+
+def accurate_mode() -> dict:
+    """Engine keyword arguments for the accurate-mode models (V4/ch_det + V4/<lang>_rec, reference
+    backend/tools/paddle_model_config.py:69-71).  V4/ch_det's activations exceed the fp16 range (LK-PAN outputs reach 1.7e5);
+    the fp32 tensor-core mode scales every convolution's operands by its calibrated power of two (calibration/V4__ch_det.json),
+    so the same mode serves it."""
+    return dict(precision=PRECISION_FP32_TC)
 
 
 def device_count() -> int:
@@ -121,6 +136,7 @@ class Engine:
         cfg.flags = flags
         self.cfg = cfg
         self.max_text_len = max_text_len
+        self._rows_per_frame = max(1, max_boxes_per_frame)     # result rows offered per frame (grown on VSE_ERR_CAPACITY)
         self._h = C.c_void_p()
         rc = self.lib.vse_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
@@ -146,6 +162,23 @@ class Engine:
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
         self._check(self.lib.vse_load_plan(self._h, which, C.cast(buf, C.c_void_p), len(blob)), "vse_load_plan")
         self.plan_names[which] = name
+        if name:
+            self._apply_calibration(which, name)
+
+    def _apply_calibration(self, which: int, name: str):
+        """Calibrated per-step input ranges (calibration/<model>.json, tools/calibrate_ranges.py) for the fp32 tensor-core mode."""
+        import json
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "calibration",
+                            "__".join(name.replace("\\", "/").rstrip("/").split("/")[-2:]) + ".json")
+        if not os.path.exists(path):
+            return
+        with open(path) as f:
+            cal = json.load(f)
+        arr = np.zeros(int(cal["n_steps"]), np.float32)
+        for k, v in cal["conv_input_absmax"].items():
+            arr[int(k)] = v
+        self._check(self.lib.vse_set_conv_input_ranges(self._h, which, arr.ctypes.data_as(C.POINTER(C.c_float)), len(arr)),
+                    "vse_set_conv_input_ranges")
 
     @property
     def tc_launch_count(self) -> int:
@@ -157,31 +190,45 @@ class Engine:
 
     # -- hot path --------------------------------------------------------- #
     def _run(self, frames: Sequence, heights, widths, strides, mem_kind: int, det_only: bool) -> Tuple[List[FrameResult], np.ndarray]:
+        """One vse_run / vse_det_only call.  The result buffers are caller-owned (C-ABI contract); when the engine reports
+        VSE_ERR_CAPACITY (more boxes than rows, or a line longer than max_text_len symbols) they are grown and the call is
+        repeated — upstream keeps up to 1000 candidates per frame (DBPostProcess max_candidates) and never fails on a dense
+        frame, so neither does this binding."""
         n = len(frames)
-        cap = max(1, n * int(self.cfg.max_boxes_per_frame))
-        T = self.max_text_len
-        # result buffers are caller-owned (C-ABI contract); keep one set per engine and batch size instead of allocating
-        # and zero-filling ~2 MB per call — the engine writes every field it reports a count for
-        key = (n, cap, T)
-        if getattr(self, "_res_key", None) != key:
-            self._res_key = key
-            self._res_buf = (np.zeros(max(n, 1), np.int32), np.zeros((cap, 4, 2), np.float32), np.zeros(cap, np.float32),
-                             np.zeros((cap, T), np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32),
-                             np.zeros(cap, np.int32))
-        n_boxes, quads, det_score, ids, id_len, rec_score, rec_width = self._res_buf
-        n_boxes[:] = 0
-        res = VseResult()
-        res.box_capacity, res.max_text_len = cap, T
-        as_p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-        res.n_boxes, res.quads, res.det_score = as_p(n_boxes, C.c_int32), as_p(quads, C.c_float), as_p(det_score, C.c_float)
-        res.ids, res.id_len, res.rec_score = as_p(ids, C.c_int32), as_p(id_len, C.c_int32), as_p(rec_score, C.c_float)
-        res.rec_width = as_p(rec_width, C.c_int32)
         ptrs = (C.c_void_p * max(n, 1))(*[int(p) for p in frames])
         h, w = _i32(heights), _i32(widths)
         st = _i32(strides) if strides is not None else None
+        as_p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
         fn = self.lib.vse_det_only if det_only else self.lib.vse_run
-        rc = fn(self._h, ptrs, as_p(h, C.c_int32), as_p(w, C.c_int32), as_p(st, C.c_int32) if st is not None else None, n,
-                mem_kind, C.byref(res))
+        for attempt in range(8):
+            cap = max(1, n * int(self._rows_per_frame))
+            T = self.max_text_len
+            # keep one set of buffers per engine and batch size instead of allocating and zero-filling ~2 MB per call — the
+            # engine writes every field it reports a count for
+            key = (n, cap, T)
+            if getattr(self, "_res_key", None) != key:
+                self._res_key = key
+                self._res_buf = (np.zeros(max(n, 1), np.int32), np.zeros((cap, 4, 2), np.float32), np.zeros(cap, np.float32),
+                                 np.zeros((cap, T), np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32),
+                                 np.zeros(cap, np.int32))
+            n_boxes, quads, det_score, ids, id_len, rec_score, rec_width = self._res_buf
+            n_boxes[:] = 0
+            res = VseResult()
+            res.box_capacity, res.max_text_len = cap, T
+            res.n_boxes, res.quads, res.det_score = as_p(n_boxes, C.c_int32), as_p(quads, C.c_float), as_p(det_score, C.c_float)
+            res.ids, res.id_len, res.rec_score = as_p(ids, C.c_int32), as_p(id_len, C.c_int32), as_p(rec_score, C.c_float)
+            res.rec_width = as_p(rec_width, C.c_int32)
+            rc = fn(self._h, ptrs, as_p(h, C.c_int32), as_p(w, C.c_int32), as_p(st, C.c_int32) if st is not None else None, n,
+                    mem_kind, C.byref(res))
+            if rc == -3 and attempt < 7:      # VSE_ERR_CAPACITY
+                msg = self.lib.vse_last_error(self._h).decode()
+                if "max_text_len" in msg and self.max_text_len < 8192:
+                    self.max_text_len *= 4
+                    continue
+                if "box_capacity" in msg and self._rows_per_frame < 1000:
+                    self._rows_per_frame = min(1000, self._rows_per_frame * 4)
+                    continue
+            break
         self._check(rc, "vse_det_only" if det_only else "vse_run")
         out: List[FrameResult] = []
         row = 0

@@ -1,0 +1,250 @@
+"""Whole-video jobs on the engine: frame feed -> vse_run batches -> raw.txt lines -> de-dup -> .srt text.
+
+SURVEY.md §8 (f): the callers either side of the predictor path, wired to the CUDA engine (the per-frame arithmetic stays in
+csrc/; this module only moves frames in and result records out):
+
+* `FrameFeed` — (f)1: the reference decodes one frame per OCR task (`ocr_task_producer`, reference
+  backend/tools/subtitle_ocr.py:164-208: seek + read) or walks the video with `cap.read()` (`extract_frame_by_fps` /
+  `extract_frame_by_det`, backend/main.py:228-251, 275-283).  Here ONE decoder thread reads the rank's frame range
+  sequentially into a ring of pinned batches; the consumer issues `vse_prefetch` for batch k+1 before `vse_run` of batch k,
+  so decode, host->device copy and kernels overlap.  The half-frame crop of `frame_preprocess` (subtitle_ocr.py:270-289) is a
+  zero-copy view (frames.sub_area_view).
+* `fast_mode_job` — BASELINE configs[0]/[3]: `extract_frame_by_fps` schedule -> `vse_run` -> rawtxt.lines_from_frame_result
+  (`OcrRecogniser.predict` order + `extract_subtitles` filter) -> shard.gather_by_frame -> dedup.remove_duplicates -> srt_text.
+* `accurate_mode_job` — BASELINE configs[2]/[4]: det + rec over EVERY frame in large batches, then the reference's
+  `extract_frame_by_det` decisions as a replay (accurate.accurate_mode_tasks) -> the same raw.txt / de-dup / .srt tail.
+
+Frames shard by contiguous ranges over the ranks (shard.frame_range); the only exchange is the gather of result lines.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import accurate, dedup, frames as F, rawtxt, shard
+from .rawtxt import Coordinate
+
+
+def default_sub_area(h: int, w: int) -> Coordinate:
+    """(xmin, xmax, ymin, ymax) of the reference's default subtitle area: fractions 0.78 / 0.99 / 0.05 / 0.95 (config.py:49)."""
+    return int(w * 0.05), int(w * 0.95), int(h * 0.78), int(h * 0.99)
+
+
+@dataclass
+class Batch:
+    numbers: List[int]            # 1-based frame numbers, as the reference counts them
+    slot: int
+    array: np.ndarray             # [n, H, W, 3] uint8 view of the pinned slot
+    ptrs: List[int] = field(default_factory=list)
+
+
+class FrameFeed:
+    """Sequential batched decode of frames [first, last] (1-based, inclusive) of one video into pinned ring buffers.
+
+    `wanted`: the frame numbers to deliver (None = every frame of the range).  The decoder thread seeks once to the range
+    start (cv2 CAP_PROP_POS_FRAMES, what the reference's producer does per task) and then only reads forward."""
+
+    def __init__(self, path: str, first: int, last: int, wanted: Optional[Sequence[int]] = None, batch: int = 32, slots: int = 3,
+                 pinned: bool = True, half: Optional[str] = None, open_capture: Optional[Callable] = None):
+        import cv2
+        self._open = open_capture or (lambda p: cv2.VideoCapture(p))
+        cap = self._open(path)
+        if not cap.isOpened():
+            raise RuntimeError(f"cannot open {path}")
+        self.fps = cap.get(cv2.CAP_PROP_FPS)
+        self.frame_count = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        self.h, self.w = int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)), int(cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+        cap.release()
+        self.path, self.first, self.last, self.batch = path, first, last, batch
+        self.wanted = None if wanted is None else sorted(k for k in wanted if first <= k <= last)
+        self.rows = F.half_frame_rows(half, self.h)
+        self.slots = []
+        for _ in range(slots):
+            if pinned:
+                import torch                      # container for page-locked host memory only
+                self.slots.append(torch.empty((batch, self.h, self.w, 3), dtype=torch.uint8, pin_memory=True).numpy())
+            else:
+                self.slots.append(np.empty((batch, self.h, self.w, 3), np.uint8))
+        self._free: "queue.Queue[int]" = queue.Queue()
+        for s in range(slots):
+            self._free.put(s)
+        self._ready: "queue.Queue[Optional[Batch]]" = queue.Queue()
+        self.frames_read = 0
+        self._err: Optional[BaseException] = None
+        self._thread = threading.Thread(target=self._decode, daemon=True)
+        self._thread.start()
+
+    def _decode(self):
+        import cv2
+        try:
+            cap = self._open(self.path)
+            if self.first > 1:
+                cap.set(cv2.CAP_PROP_POS_FRAMES, self.first - 1)
+            want = None if self.wanted is None else set(self.wanted)
+            stop = self.last if want is None else (max(want) if want else 0)
+            no = self.first - 1
+            cur: Optional[Batch] = None
+            while no < stop:
+                ok, frame = cap.read()
+                if not ok:
+                    break
+                no += 1
+                self.frames_read += 1
+                if want is not None and no not in want:
+                    continue
+                if cur is None:
+                    s = self._free.get()
+                    cur = Batch([], s, self.slots[s])
+                cur.array[len(cur.numbers)] = frame
+                cur.numbers.append(no)
+                if len(cur.numbers) == self.batch:
+                    self._ready.put(cur)
+                    cur = None
+            if cur is not None and cur.numbers:
+                self._ready.put(cur)
+            cap.release()
+        except BaseException as e:          # surfaced in the consumer
+            self._err = e
+        self._ready.put(None)
+
+    def view(self, b: Batch):
+        """(ptrs, heights, widths, strides) of the batch's frames — or of their half-frame views — for vse_run / vse_prefetch."""
+        r0, r1 = self.rows
+        n = len(b.numbers)
+        stride = self.w * 3
+        base = b.array.ctypes.data
+        ptrs = [base + j * self.h * stride + r0 * stride for j in range(n)]
+        return ptrs, [r1 - r0] * n, [self.w] * n, [stride] * n
+
+    def release(self, b: Batch):
+        self._free.put(b.slot)
+
+    def __iter__(self) -> Iterator[Batch]:
+        while True:
+            b = self._ready.get()
+            if b is None:
+                if self._err is not None:
+                    raise self._err
+                return
+            yield b
+
+
+def run_feed(engine, feed: FrameFeed, det_only: bool = False, mem_kind: Optional[int] = None) -> Dict[int, object]:
+    """Every delivered frame through vse_run (det_only: vse_det_only) with one batch of look-ahead on the copy stream.
+    -> {frame number: engine.FrameResult}."""
+    from . import engine as E
+    mk = E.MEM_PINNED if mem_kind is None else mem_kind
+    out: Dict[int, object] = {}
+    it = iter(feed)
+    cur = next(it, None)
+    while cur is not None:
+        nxt = next(it, None)                       # decoded (or being decoded) while the current batch computes
+        if nxt is not None:
+            engine.prefetch(*feed.view(nxt)[:4], mem_kind=mk)
+        ptrs, hs, ws, st = feed.view(cur)
+        res = engine.run_device(ptrs, hs, ws, st, det_only=det_only, mem_kind=mk)
+        for no, r in zip(cur.numbers, res):
+            out[no] = r
+        feed.release(cur)
+        cur = nxt
+    return out
+
+
+def _srt(lines: List[str], fps: float, path: str, threshold: float) -> Tuple[List[Tuple[str, str, str]], str]:
+    import cv2
+    subs = dedup.remove_duplicates(lines, threshold, use_vsf=False)
+    cap = cv2.VideoCapture(path)
+
+    def pos_msec(frame_no):                        # the decoder calls of _frame_to_timecode (reference backend/main.py:738-742)
+        cap.set(cv2.CAP_PROP_POS_FRAMES, frame_no)
+        ok, _ = cap.read()
+        return cap.get(cv2.CAP_PROP_POS_MSEC) if ok else None
+
+    text, _ = dedup.srt_text(subs, fps, pos_msec)
+    cap.release()
+    return subs, text
+
+
+@dataclass
+class JobResult:
+    lines: List[str]                       # raw.txt lines of the whole video, frame-ordered (every rank holds them)
+    subtitles: List[Tuple[str, str, str]]
+    srt: str
+    frames_ocr: int                        # frames this rank pushed through the engine
+    frame_numbers: List[int]               # ... and their numbers
+    results: Dict[int, object]
+
+
+def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, world: int = 1, batch: int = 32,
+                  sub_area: Optional[Coordinate] = "default", rec_char_type: str = "en", drop_score: float = 0.75,
+                  extract_frequency: int = 3, threshold: float = 0.8, half: Optional[str] = None, pinned: bool = True,
+                  write_srt: bool = True) -> JobResult:
+    """Fast mode of the reference (`run` -> `extract_frame_by_fps`, backend/main.py:145-147) on this rank's share of the
+    schedule.  `sub_area` 'default' = the reference's default area for the video's size; None = no area."""
+    probe = FrameFeed(path, 1, 0, [], batch=1, slots=1, pinned=False)
+    schedule = F.fast_mode_frames(probe.frame_count, probe.fps, extract_frequency)
+    lo, hi = shard.frame_range(rank, world, len(schedule))
+    mine = schedule[lo:hi]
+    if sub_area == "default":
+        sub_area = default_sub_area(probe.h, probe.w)
+    results: Dict[int, object] = {}
+    if mine:
+        feed = FrameFeed(path, mine[0], mine[-1], mine, batch=batch, pinned=pinned, half=half)
+        results = run_feed(engine, feed)
+    local = []
+    for no in sorted(results):
+        ls = rawtxt.lines_from_frame_result(no, results[no], characters, sub_area=sub_area, rec_char_type=rec_char_type,
+                                            drop_score=drop_score)
+        local.append((no, ls))
+    merged = shard.gather_by_frame(local)
+    lines = [l for _, ls in merged for l in ls]
+    subs, text = _srt(lines, probe.fps, path, threshold) if write_srt else ([], "")
+    return JobResult(lines, subs, text, len(results), sorted(results), results)
+
+
+def accurate_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, world: int = 1, batch: int = 64,
+                      sub_area: Optional[Coordinate] = "default", rec_char_type: str = "ch", drop_score: float = 0.75,
+                      threshold: float = 0.8, first: int = 1, last: Optional[int] = None, pinned: bool = True,
+                      write_srt: bool = True) -> JobResult:
+    """Accurate mode of the reference (`extract_frame_by_det`, backend/main.py:255-376): the detector looks at EVERY frame and
+    the recogniser reads the frames the controller asks for.  Here det + rec run over every frame of this rank's range in
+    batches (`vse_run`), the records are gathered by frame number and the reference's decisions are replayed
+    (accurate.accurate_mode_tasks) — so the queued tasks, their cached results and the raw.txt lines come out as the
+    reference's own loop produces them.  [first, last]: optional stretch of the video (frame numbers stay the video's)."""
+    from .charset import ids_to_text
+    probe = FrameFeed(path, 1, 0, [], batch=1, slots=1, pinned=False)
+    last = probe.frame_count if last is None else min(last, probe.frame_count)
+    n = last - first + 1
+    lo, hi = shard.frame_range(rank, world, n)
+    if sub_area == "default":
+        sub_area = default_sub_area(probe.h, probe.w)
+    results: Dict[int, object] = {}
+    if hi > lo:
+        feed = FrameFeed(path, first + lo, first + hi - 1, None, batch=batch, pinned=pinned)
+        results = run_feed(engine, feed)
+    local = [(no, ([q.tolist() for q in r.quads], [(ids_to_text(i, characters), float(s)) for i, s in zip(r.ids, r.rec_scores)]))
+             for no, r in sorted(results.items())]
+    merged = dict(shard.gather_by_frame(local))
+    delivered = max(merged) - first + 1 if merged else 0
+
+    def detect(k):
+        return merged[first + k - 1][0] if first + k - 1 in merged else []
+
+    def predict(k):
+        quads, rec = merged[first + k - 1]
+        return rawtxt.order_like_predict([np.asarray(q, np.float32) for q in quads], rec)
+
+    tasks = accurate.accurate_mode_tasks(n, detect, predict, sub_area, threshold, frames_read=delivered)
+    lines: List[str] = []
+    for k, dt_box, rec in tasks:
+        if dt_box is None:                        # the worker runs predict on the task's own frame (subtitle_ocr.py:29-30)
+            dt_box, rec = predict(k)
+        lines += rawtxt.frame_lines(first + k - 1, dt_box, rec, sub_area=sub_area, rec_char_type=rec_char_type, drop_score=drop_score)
+    subs, text = _srt(lines, probe.fps, path, threshold) if write_srt else ([], "")
+    res = JobResult(lines, subs, text, len(results), sorted(results), results)
+    res.tasks = tasks
+    return res
