@@ -53,7 +53,25 @@ def parse_args():
     ap.add_argument("--precision", default=None, choices=["fp16", "fp32", "tf32", "fp32_tc"],
                     help="activation / product precision (default: engine.bench_mode(), the mode held to the parity bar)")
     ap.add_argument("--frame-stride", type=int, default=7, help="synthetic stream index step between consecutive frames of the pool")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[k]: 1 = the headline (default); 2 = test_cn.mp4 accurate mode, V4/ch_det + V4/ch_rec, "
+                         "batch 64; 3 = four sample videos, fast mode, frame ranges sharded over the ranks (whole jobs: decode -> "
+                         ".srt); 4 = 4K synthetic 50k-frame stream, accurate models, frame-parallel")
+    ap.add_argument("--video", default=None, help="take the frames from this video (every --frame-stride-th frame) instead of the synthetic stream")
+    args = ap.parse_args()
+    vids = os.path.join(ROOT, "tests", "golden", "_videos")
+    if args.config == 2:
+        args.det, args.rec = args.det or "V4/ch_det", args.rec or "V4/ch_rec"
+        args.batch, args.height, args.width, args.pool = 64, 1080, 1440, 2
+        if args.video is None and os.path.exists(os.path.join(vids, "test_cn.mp4")):
+            args.video = os.path.join(vids, "test_cn.mp4")
+        args.frame_stride = 3
+    elif args.config == 4:
+        args.det, args.rec = args.det or "V4/ch_det", args.rec or "V4/ch_rec"
+        args.batch, args.height, args.width, args.pool = 16, 2160, 3840, 2
+        if "--steps" not in sys.argv:
+            args.steps = -(-50000 // (max(args.gpus, 1) * args.batch))      # the whole 50k-frame stream, sharded
+    return args
 
 
 def apply_model_args(args):
@@ -73,11 +91,28 @@ def frame_index(p: int, k: int, world_b: int, stride: int) -> int:
 def workload_config(args, world: int):
     """The `config` object both arms print (the driver compares them)."""
     B, H, W = args.batch, args.height, args.width
-    return {"workload": f"synthetic {H}p subtitle frames (SURVEY.md §8d generator), {DET} + {REC}",
+    src = f"frames of {os.path.basename(args.video)} (reference sample video)" if args.video else f"synthetic {H}p subtitle frames (SURVEY.md §8d generator)"
+    return {"workload": f"{src}, {DET} + {REC}", "baseline_config": args.config,
             "frames_per_step_per_gpu": B, "global_frames_per_step": world * B, "frame": [H, W, 3],
             "parallelism": f"frame-range sharding x{world}",
             "frames": f"stream index (pool_batch * {world * B} + k) * {args.frame_stride}, {args.pool} pool batches cycled",
             "l2": f"inputs larger than L2: {args.pool} distinct batches x {B * H * W * 3 / 1e6:.0f} MB cycled"}
+
+
+def video_frames_at(path: str, indices):
+    """{index: frame} for the given 0-based frame indices of a video, one sequential decode."""
+    import cv2
+    cap = cv2.VideoCapture(path)
+    need, out, no = set(indices), {}, 0
+    while need and no <= max(need):
+        ok, fr = cap.read()
+        if not ok:
+            break
+        if no in need:
+            out[no] = fr
+        no += 1
+    cap.release()
+    return out
 
 
 def env_rank():
@@ -160,12 +195,17 @@ def run_reference(args, rank, world):
     from video_subtitle_extractor_b200.synth import SynthStream
     det_blob, rec_blob = weights.load_plan_blob(DET), weights.load_plan_blob(REC)
     oracle, cores = cpu_oracle(det_blob, rec_blob)
-    per_step = 4                                     # bounded sample of the 32-frame batch per step
+    per_step = 4 if args.config == 1 else 1          # bounded sample of the batch per step (server graphs: ~12 s per frame)
     stream = SynthStream(args.height, args.width)
     # the SAME frames the B200 arm times: frames 0, 8, 16, 24 of pool batch (step mod pool) of rank 0
     B = args.batch
     pick = [k * (B // per_step) for k in range(per_step)]
-    frames = {(p, k): stream.frame(frame_index(p, k, world * B, args.frame_stride)) for p in range(args.pool) for k in pick}
+    if args.video:
+        vf = video_frames_at(args.video, [frame_index(p, k, world * B, args.frame_stride) for p in range(args.pool) for k in pick])
+        frames = {(p, k): vf[frame_index(p, k, world * B, args.frame_stride)] for p in range(args.pool) for k in pick}
+        args.height, args.width = next(iter(vf.values())).shape[:2]
+    else:
+        frames = {(p, k): stream.frame(frame_index(p, k, world * B, args.frame_stride)) for p in range(args.pool) for k in pick}
     for _ in range(max(args.warmup, 1)):
         oracle.ocr(frames[(0, 0)])
     t0 = time.perf_counter()
@@ -304,6 +344,12 @@ def run_b200(args, rank, local_rank, world):
 
     B, H, W = args.batch, args.height, args.width
     stream = SynthStream(H, W)
+    video_frames = {}
+    if args.video:      # real frames: every frame_stride-th frame of the video, decoded once up front
+        video_frames = video_frames_at(args.video, [frame_index(p, k, world * B, args.frame_stride) for p in range(args.pool)
+                                                    for k in range(world * B)])
+        H, W = next(iter(video_frames.values())).shape[:2]
+        args.height, args.width = H, W
     # rank r owns frames [r*B, (r+1)*B) of every global batch of world*B frames
     host_batches, dev_batches = [], []
     for p in range(args.pool):
@@ -312,7 +358,7 @@ def run_b200(args, rank, local_rank, world):
         pinned = torch.empty((len(idx), H, W, 3), dtype=torch.uint8, pin_memory=True)
         arr = pinned.numpy()
         for j, i in enumerate(idx):
-            arr[j] = stream.frame(i)
+            arr[j] = video_frames[i] if args.video else stream.frame(i)
         host_batches.append(pinned)
         dev_batches.append(pinned.to(dev))
     torch.cuda.synchronize()
@@ -412,24 +458,39 @@ def run_b200(args, rank, local_rank, world):
             achieved = bytes_ / (t_ms * 1e-3) / 1e9
             traffic = ncu_traffic()
             roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                        "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch") if args.config == 1 else None,
                         "peak_source": peak_src, "launches_per_step": n_launch,
                         "algorithmic_bytes_per_launch": bytes_ / n_launch, "avg_launch_ms": t_ms / n_launch,
                         "tflops": flops / (t_ms * 1e-3) / 1e12,
                         "per_kernel_ms": {k: round(t, 4) for k, t, _, _, _ in table},
                         "per_kernel_gbs": {k: round(b / max(t, 1e-6) / 1e6, 1) for k, t, b, _, _ in table}}
+        if roofline is not None and flops / max(bytes_, 1) > 215.0:
+            # the server models (309-649 FLOP/B) sit right of the ridge: tensor-pipe roofline.  ALGORITHMIC
+            # flops (one product per multiply-add; the fp32 tensor-core mode issues three MMAs per product) against the
+            # measured sustained bf16 rate
+            tpeak, tsrc = 1407.5, "fallback (SURVEY.md §8d)"
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    tpeak, tsrc = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json: bf16_tflops_sustained)"
+            except Exception:
+                pass
+            roofline.update({"bound": "tensor", "achieved": roofline["tflops"], "peak": tpeak, "unit": "TFLOP/s",
+                             "frac": roofline["tflops"] / tpeak, "peak_source": tsrc, "hbm_gbs": achieved,
+                             "note": "algorithmic FLOPs; the mode issues 3 fp16 MMAs per product (hi*Wh + lo*Wh + hi*Wl)"})
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             oracle, cores = cpu_oracle(det_blob, rec_blob)
             frames = [host_batches[0].numpy()[j] for j in range(B)]
+            if args.config != 1:
+                frames = frames[:1]      # the server graphs cost ~12 s per frame on the CPU: one frame is the bounded sample
             fps, n, dt = time_cpu(oracle, frames, args.cpu_seconds)
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n} frames = {n // B} pass(es) over the {B} frames of one step ({H}x{W}) in {dt:.1f} s: CPU restatement "
+                   "sample": f"{n} frames = {n / B:.2f} pass(es) over the {B} frames of one step ({H}x{W}) in {dt:.1f} s: CPU restatement "
                              f"of the reference path (torch-CPU fp32 + cv2), one frame per call, rec batches <= 6"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16" if mode["precision"] == E.PRECISION_FP16 else "f32", "data": "synthetic",
+            "dtype": "f16" if mode["precision"] == E.PRECISION_FP16 else "f32", "data": "real video frames" if args.video else "synthetic",
             "config": workload_config(args, world),
             "precision": prec_name + (f"; vse_config.flags={args.flags}" if args.flags else ""),
             "text_lines_per_frame": n_lines / max(args.steps * B, 1), "mean_padded_rec_width": mean_width,

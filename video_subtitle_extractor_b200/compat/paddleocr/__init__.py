@@ -32,9 +32,11 @@ class PaddleOCR:
                  det_db_box_thresh: float = 0.6, det_db_unclip_ratio: float = 1.5, gpu_id: int = 0, **ignored):
         shape = [int(v) for v in str(rec_image_shape).split(",")]
         self.drop_score = drop_score
-        # accurate mode's server detector (paddle_model_config.py:60,70) overflows fp16 activations: fp32 engine for it
-        flags = _E.FLAG_DET_TF32 if det_model_dir and _W.needs_fp32(det_model_dir) else 0
-        self.engine = _E.Engine(device=gpu_id, flags=flags, rec_image_h=shape[1], rec_image_w=shape[2], rec_batch_num=rec_batch_num,
+        # one mode for every shipped model: fp32 activations, tensor-core products on fp16 hi/lo splits scaled per layer
+        # (engine.bench_mode(): the mode the parity tests hold to the reference's results; the accurate-mode server detector,
+        # paddle_model_config.py:60,70, exceeds the fp16 range and runs through its calibrated per-layer scales)
+        self.engine = _E.Engine(device=gpu_id, rec_image_h=shape[1], rec_image_w=shape[2], rec_batch_num=rec_batch_num,
+                                **_E.bench_mode(),
                                 det_limit_side_len=det_limit_side_len, det_thresh=det_db_thresh,
                                 det_box_thresh=det_db_box_thresh, det_unclip_ratio=det_db_unclip_ratio)
         self.engine.load_plan(_E.PLAN_DET, _plan_for(det_model_dir), det_model_dir)

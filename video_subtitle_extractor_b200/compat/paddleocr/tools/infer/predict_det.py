@@ -11,8 +11,7 @@ from paddleocr import _plan_for
 
 class TextDetector:
     def __init__(self, args):
-        flags = _E.FLAG_DET_TF32 if _W.needs_fp32(args.det_model_dir) else 0
-        self.engine = _E.Engine(device=getattr(args, "gpu_id", 0), flags=flags, det_limit_side_len=args.det_limit_side_len,
+        self.engine = _E.Engine(device=getattr(args, "gpu_id", 0), det_limit_side_len=args.det_limit_side_len, **_E.bench_mode(),
                                 det_thresh=args.det_db_thresh, det_box_thresh=args.det_db_box_thresh,
                                 det_unclip_ratio=args.det_db_unclip_ratio)
         self.engine.load_plan(_E.PLAN_DET, _plan_for(args.det_model_dir), args.det_model_dir)

@@ -34,14 +34,14 @@ struct Engine::Pipeline {
     // pending list and the choice of staging buffer; `busy` is the buffer the running batch reads (never handed out)
     std::mutex mu;
     int busy = -1;
-    DevBuf labels, slot_of, n_comp, roots, bbox, order, cand, status, n_boxes, quads, scores, blk_fg;
+    DevBuf labels, slot_of, n_comp, roots, bbox, order, cand, status, n_boxes, quads, scores, blk_fg, blabels, bopen, blk_listed, ckey;
     DevBuf cubic_tab, crop_jobs, crop_buf, rec_jobs, rec_in;
     DevBuf ctc_meta, ctc_ids, ctc_len, ctc_score;
     PinnedBuf h_in, h_out;
     cudaEvent_t ev[9] = {};
     bool ev_ready = false, tab_ready = false;
     std::vector<DevBuf*> all() {
-        return {&fbuf[0], &fbuf[1], &dbg_frames, &det_in, &jobs, &det_frames, &labels, &slot_of, &n_comp, &roots, &bbox, &order, &cand, &status, &blk_fg,
+        return {&fbuf[0], &fbuf[1], &dbg_frames, &det_in, &jobs, &det_frames, &labels, &slot_of, &n_comp, &roots, &bbox, &order, &cand, &status, &blk_fg, &blabels, &bopen, &blk_listed, &ckey,
                 &n_boxes, &quads, &scores, &cubic_tab, &crop_jobs, &crop_buf, &rec_jobs, &rec_in, &ctc_meta, &ctc_ids,
                 &ctc_len, &ctc_score};
     }
@@ -118,6 +118,10 @@ static DbWorkspace make_ws(Engine::Pipeline* p) {
     DbWorkspace ws;
     ws.labels = p->labels.as<int>();
     ws.slot_of = p->slot_of.as<int>();
+    ws.blabels = p->blabels.as<int>();
+    ws.bopen = p->bopen.as<int>();
+    ws.blk_listed = p->blk_listed.as<int>();
+    ws.ckey = p->ckey.as<int>();
     ws.fg_count = p->blk_fg.as<int>();
     ws.fg_list = p->blk_fg.as<int>() + 4;
     ws.n_comp = p->n_comp.as<int>();
@@ -152,6 +156,10 @@ void Engine::db_post_device(const float* prob, const std::vector<DetFrame>& fram
     P->labels.reserve(total * sizeof(int));
     P->slot_of.reserve(total * sizeof(int));
     P->blk_fg.reserve((size_t(n) * ((max_rh + 7) / 8) * ((max_rw + 31) / 32) + 4) * sizeof(int));
+    P->blabels.reserve(total * sizeof(int));
+    P->bopen.reserve(total * sizeof(int));
+    P->blk_listed.reserve(size_t(n) * ((max_rh + 7) / 8) * ((max_rw + 31) / 32) * sizeof(int));
+    P->ckey.reserve(size_t(n) * kSlotCap * sizeof(int));
     P->n_comp.reserve(n * sizeof(int));
     P->status.reserve(n * sizeof(int));
     P->roots.reserve(size_t(n) * kSlotCap * sizeof(int));

@@ -8,8 +8,11 @@
 // The per-candidate arithmetic lives in dbpost_core.cuh / geom.cuh and is unit-tested on the CPU against cv2.
 // Compiled with --fmad=false: OpenCV's float code is not FMA-contracted and box corners must match bit for bit.
 //
-// Scope note: cv2.findContours(RETR_LIST) also reports hole borders; a hole contour only survives upstream when its
-// own box scores >= 0.6 and is >= 5 px after unclip.  Holes are not traced here (documented in DESIGN.md).
+// cv2.findContours(RETR_LIST) also reports HOLE borders (the foreground pixels 4-adjacent to an enclosed background
+// region); upstream treats them like any contour, and on real video some survive the score / size filters (frame 1391 of
+// the reference's test_cn.mp4 yields two such boxes).  They are found here by labelling the background of the blocks that
+// hold foreground (4-connectivity) and keeping the components that never reach the image border or a block without
+// foreground; such a component that swallowed a whole empty block could only score far below box_thresh and is dropped.
 #include "postproc.cuh"
 #include "pdl.cuh"
 
@@ -54,7 +57,8 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 // run inside that 32-pixel segment (one ballot, no chains along rows)
 __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ prob, const DetFrame* __restrict__ frames,
                                                      float thresh, int* __restrict__ labels, int* __restrict__ status,
-                                                     int* __restrict__ fg_count, int* __restrict__ fg_list) {
+                                                     int* __restrict__ fg_count, int* __restrict__ fg_list,
+                                                     int* __restrict__ blabels, int* __restrict__ bopen, int* __restrict__ blk_listed) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
     const DetFrame fr = frames[blockIdx.z];
@@ -75,20 +79,36 @@ __global__ void __launch_bounds__(256) db_label_init(const float* __restrict__ p
     if (any && threadIdx.x == 0 && threadIdx.y == 0) {
         const int slot = atomicAdd(fg_count, 1);      // order of the list does not matter: the passes below are order-free
         fg_list[slot] = (blockIdx.z << 20) | (blockIdx.y << 10) | blockIdx.x;
+        blk_listed[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 1;
     }
     if (!in) return;
+    const int lane = threadIdx.x;
     if (fg) {
-        const int lane = threadIdx.x;
         const unsigned below = ~mask & ((1u << lane) - 1u);
         const int start = below ? (32 - __clz(below)) : 0;
         labels[g] = g - (lane - start);
     } else {
         labels[g] = -1;
     }
+    if (any) {   // background labels of a listed block: start of the pixel's background run inside the 32-pixel segment
+        if (fg) {
+            blabels[g] = -1;
+        } else {
+            const unsigned below = mask & ((1u << lane) - 1u);
+            const int start = below ? (32 - __clz(below)) : 0;
+            blabels[g] = g - (lane - start);
+        }
+        bopen[g] = 0;
+    }
+}
+
+__device__ __forceinline__ bool blk_is_listed(const int* __restrict__ blk_listed, int f, int gx, int gy, int x, int y) {
+    return blk_listed[(f * gy + (y >> 3)) * gx + (x >> 5)] != 0;
 }
 
 __global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict__ frames, int* labels,
-                                                      const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+                                                      const int* __restrict__ fg_count, const int* __restrict__ fg_list,
+                                                      int* blabels, const int* __restrict__ blk_listed, int gx, int gy) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
   const int n_fg = *fg_count;
@@ -98,7 +118,14 @@ __global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict
     const int x = bx * 32 + threadIdx.x, y = by * blockDim.y + threadIdx.y;
     if (x >= fr.rw || y >= fr.rh) continue;
     const int g = fr.map_off + y * fr.rw + x;
-    if (labels[g] < 0) continue;
+    if (labels[g] < 0) {
+        // background, 4-connectivity: the run inside the segment is already one label; join across the segment boundary and
+        // with the pixel above — where that neighbour lies in a listed block (otherwise the component is open: db_label_flatten)
+        if (threadIdx.x == 0 && x > 0 && blk_is_listed(blk_listed, bz, gx, gy, x - 1, y) && blabels[g - 1] >= 0) uf_union(blabels, g, g - 1);
+        if (y > 0 && (threadIdx.y != 0 || blk_is_listed(blk_listed, bz, gx, gy, x, y - 1)) && blabels[g - fr.rw] >= 0)
+            uf_union(blabels, g, g - fr.rw);
+        continue;
+    }
     const int rw = fr.rw;
     const bool W = x > 0 && labels[g - 1] >= 0;
     const bool up = y > 0;
@@ -121,7 +148,8 @@ __global__ void __launch_bounds__(256) db_label_merge(const DetFrame* __restrict
 
 __global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restrict__ frames, int* labels, int* slot_of,
                                                         int* n_comp, int* roots, int* bbox,
-                                                        const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+                                                        const int* __restrict__ fg_count, const int* __restrict__ fg_list,
+                                                        int* blabels, int* bopen, const int* __restrict__ blk_listed, int gx, int gy) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
   const int n_fg = *fg_count;
@@ -131,7 +159,16 @@ __global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restri
     const int x = bx * 32 + threadIdx.x, y = by * blockDim.y + threadIdx.y;
     if (x >= fr.rw || y >= fr.rh) continue;
     const int g = fr.map_off + y * fr.rw + x;
-    if (labels[g] < 0) continue;
+    if (labels[g] < 0) {
+        const int r = uf_find(blabels, g);
+        blabels[g] = r;
+        // reaches the image border (cv2 frames the image with background) or a block without foreground: not a hole
+        const bool open = x == 0 || y == 0 || x == fr.rw - 1 || y == fr.rh - 1 ||
+                          !blk_is_listed(blk_listed, f, gx, gy, x - 1, y) || !blk_is_listed(blk_listed, f, gx, gy, x + 1, y) ||
+                          !blk_is_listed(blk_listed, f, gx, gy, x, y - 1) || !blk_is_listed(blk_listed, f, gx, gy, x, y + 1);
+        if (open) bopen[r] = 1;
+        continue;
+    }
     const int r = uf_find(labels, g);
     labels[g] = r;
     if (r == g) {
@@ -148,9 +185,38 @@ __global__ void __launch_bounds__(256) db_label_flatten(const DetFrame* __restri
   }
 }
 
+// closed background components become contours of their own (hole borders)
+__global__ void __launch_bounds__(256) db_hole_slots(const DetFrame* __restrict__ frames, const int* __restrict__ labels,
+                                                     const int* __restrict__ blabels, const int* __restrict__ bopen, int* slot_of,
+                                                     int* n_comp, int* roots, int* bbox, const int* __restrict__ fg_count,
+                                                     const int* __restrict__ fg_list) {
+    pdl_wait();
+    pdl_trigger();
+  const int n_fg = *fg_count;
+  for (int it = blockIdx.x; it < n_fg; it += gridDim.x) {
+    const int code = fg_list[it], f = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
+    const DetFrame fr = frames[f];
+    const int x = bx * 32 + threadIdx.x, y = by * blockDim.y + threadIdx.y;
+    if (x >= fr.rw || y >= fr.rh) continue;
+    const int g = fr.map_off + y * fr.rw + x;
+    if (labels[g] >= 0 || blabels[g] != g) continue;
+    if (bopen[g]) { slot_of[g] = -1; continue; }
+    const int slot = atomicAdd(&n_comp[f], 1);
+    if (slot < kSlotCap) {
+        roots[f * kSlotCap + slot] = g | kHoleFlag;
+        slot_of[g] = slot;
+        int* b = bbox + (size_t(f) * kSlotCap + slot) * 4;
+        b[0] = x; b[1] = y; b[2] = x; b[3] = y;
+    } else {
+        slot_of[g] = -1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ frames, const int* __restrict__ labels,
                                                const int* __restrict__ slot_of, int* bbox,
-                                               const int* __restrict__ fg_count, const int* __restrict__ fg_list) {
+                                               const int* __restrict__ fg_count, const int* __restrict__ fg_list,
+                                               const int* __restrict__ blabels) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
   const int n_fg = *fg_count;
@@ -161,7 +227,14 @@ __global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ fram
     if (x >= fr.rw || y >= fr.rh) continue;
     const int g = fr.map_off + y * fr.rw + x;
     const int r = labels[g];
-    if (r < 0) continue;
+    if (r < 0) {
+        const int slot = slot_of[blabels[g]];      // hole pixels are few: every one updates the box of its hole
+        if (slot >= 0) {
+            int* b = bbox + (size_t(f) * kSlotCap + slot) * 4;
+            atomicMin(b + 0, x); atomicMin(b + 1, y); atomicMax(b + 2, x); atomicMax(b + 3, y);
+        }
+        continue;
+    }
     const bool W = x > 0 && labels[g - 1] >= 0;
     const bool E = x + 1 < fr.rw && labels[g + 1] >= 0;
     if (W && E) continue;
@@ -177,9 +250,11 @@ __global__ void __launch_bounds__(256) db_bbox(const DetFrame* __restrict__ fram
   }
 }
 
-// cv2.findContours(RETR_LIST) returns contours in reverse discovery order: descending root (raster) index
+// cv2.findContours(RETR_LIST) returns contours in reverse discovery order.  The raster scan discovers an outer border at the
+// component's first pixel and a hole border at the pixel LEFT of the hole's first pixel (outer border first when both start
+// at the same pixel): key = 2 * start pixel (+ 1 for a hole), descending.
 __global__ void __launch_bounds__(256) db_sort_components(const int* __restrict__ n_comp, const int* __restrict__ roots,
-                                                          int* order, int* status) {
+                                                          int* order, int* status, int* ckey) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
     const int f = blockIdx.x;
@@ -189,10 +264,16 @@ __global__ void __launch_bounds__(256) db_sort_components(const int* __restrict_
         n = kSlotCap;
     }
     const int* r = roots + size_t(f) * kSlotCap;
+    int* key = ckey + size_t(f) * kSlotCap;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int mine = r[t];
+        const int v = r[t];
+        key[t] = (v & kHoleFlag) ? 2 * ((v & ~kHoleFlag) - 1) + 1 : 2 * v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int mine = key[t];
         int rank = 0;
-        for (int j = 0; j < n; j++) rank += r[j] > mine;
+        for (int j = 0; j < n; j++) rank += key[j] > mine;
         order[size_t(f) * kSlotCap + rank] = t;
     }
 }
@@ -211,7 +292,9 @@ size_t db_candidate_smem_bytes(int max_rh) {
 __global__ void __launch_bounds__(kCandThreads) db_candidates(const float* __restrict__ prob, const DetFrame* __restrict__ frames,
                                                               const int* __restrict__ labels, const int* __restrict__ n_comp,
                                                               const int* __restrict__ roots, const int* __restrict__ bbox,
-                                                              const int* __restrict__ order, DbParams p, int max_rh, float* cand) {
+                                                              const int* __restrict__ order, DbParams p, int max_rh, float* cand,
+                                                              const int* __restrict__ blabels, const int* __restrict__ blk_listed,
+                                                              int gx, int gy) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
     extern __shared__ __align__(16) unsigned char smem[];
@@ -231,12 +314,35 @@ __global__ void __launch_bounds__(kCandThreads) db_candidates(const float* __res
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = blockIdx.x; k < n; k += gridDim.x) {
         const int slot = order[size_t(f) * kSlotCap + k];
-        const int root = roots[size_t(f) * kSlotCap + slot];
+        const int root_raw = roots[size_t(f) * kSlotCap + slot];
+        const bool hole = (root_raw & kHoleFlag) != 0;
+        const int root = root_raw & ~kHoleFlag;
         const int* b = bbox + (size_t(f) * kSlotCap + slot) * 4;
-        const int xmin = b[0], ymin = b[1], xmax = b[2], ymax = b[3];
+        int xmin = b[0], ymin = b[1], xmax = b[2], ymax = b[3];
+        if (hole) {
+            // hole border = the foreground pixels 4-adjacent to the hole's pixels: one row / column around the hole's box (a
+            // closed background component never touches the image border, so the ring is inside the map)
+            const int hx0 = xmin, hy0 = ymin, hx1 = xmax, hy1 = ymax;
+            ymin -= 1; ymax += 1;
+            const int rows_h = ymax - ymin + 1;
+            for (int r = threadIdx.x; r < rows_h; r += kCandThreads) { xl[r] = INT_MAX; xr[r] = -1; }
+            __syncthreads();
+            const int hw = hx1 - hx0 + 1, hn = hw * (hy1 - hy0 + 1);
+            for (int i = threadIdx.x; i < hn; i += kCandThreads) {
+                const int y = hy0 + i / hw, x = hx0 + i % hw;
+                if (!blk_is_listed(blk_listed, f, gx, gy, x, y)) continue;      // labels of unlisted blocks are stale
+                const int g = fr.map_off + y * fr.rw + x;
+                if (blabels[g] != root) continue;
+                const int r = y - ymin;
+                if (labels[g - 1] >= 0) { atomicMin(&xl[r], x - 1); atomicMax(&xr[r], x - 1); }
+                if (labels[g + 1] >= 0) { atomicMin(&xl[r], x + 1); atomicMax(&xr[r], x + 1); }
+                if (labels[g - fr.rw] >= 0) { atomicMin(&xl[r - 1], x); atomicMax(&xr[r - 1], x); }
+                if (labels[g + fr.rw] >= 0) { atomicMin(&xl[r + 1], x); atomicMax(&xr[r + 1], x); }
+            }
+        }
         const int rows = ymax - ymin + 1;
         // per-row extents of the component inside its bounding box
-        for (int r = warp; r < rows; r += kCandThreads / 32) {
+        for (int r = warp; r < rows && !hole; r += kCandThreads / 32) {
             const int* L = labels + fr.map_off + (ymin + r) * fr.rw;
             int lo = INT_MAX, hi = -1;
             for (int x0 = xmin; x0 <= xmax; x0 += 32) {
@@ -366,12 +472,18 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
     // machine-sized grid (subtitle maps are > 99 % background, and launching 65 k empty blocks costs more than the work)
     if (grid.x > 1023 || grid.y > 1023 || n_frames > 2047) return;   // list code = frame << 20 | block_y << 10 | block_x (checked by the caller)
     cudaMemsetAsync(ws.fg_count, 0, sizeof(int), st);
-    pdl_launch(db_label_init, grid, blk, 0, st, prob, frames_dev, p.thresh, ws.labels, ws.status, ws.fg_count, ws.fg_list);
+    const int gx = int(grid.x), gy = int(grid.y);
+    cudaMemsetAsync(ws.blk_listed, 0, sizeof(int) * size_t(n_frames) * gx * gy, st);
+    pdl_launch(db_label_init, grid, blk, 0, st, prob, frames_dev, p.thresh, ws.labels, ws.status, ws.fg_count, ws.fg_list,
+               ws.blabels, ws.bopen, ws.blk_listed);
     const int pgrid = 148 * 4;
-    pdl_launch(db_label_merge, pgrid, blk, 0, st, frames_dev, ws.labels, ws.fg_count, ws.fg_list);
-    pdl_launch(db_label_flatten, pgrid, blk, 0, st, frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox, ws.fg_count, ws.fg_list);
-    pdl_launch(db_bbox, pgrid, blk, 0, st, frames_dev, ws.labels, ws.slot_of, ws.bbox, ws.fg_count, ws.fg_list);
-    pdl_launch(db_sort_components, n_frames, 256, 0, st, ws.n_comp, ws.roots, ws.order, ws.status);
+    pdl_launch(db_label_merge, pgrid, blk, 0, st, frames_dev, ws.labels, ws.fg_count, ws.fg_list, ws.blabels, ws.blk_listed, gx, gy);
+    pdl_launch(db_label_flatten, pgrid, blk, 0, st, frames_dev, ws.labels, ws.slot_of, ws.n_comp, ws.roots, ws.bbox, ws.fg_count,
+               ws.fg_list, ws.blabels, ws.bopen, ws.blk_listed, gx, gy);
+    pdl_launch(db_hole_slots, pgrid, blk, 0, st, frames_dev, ws.labels, ws.blabels, ws.bopen, ws.slot_of, ws.n_comp, ws.roots, ws.bbox,
+               ws.fg_count, ws.fg_list);
+    pdl_launch(db_bbox, pgrid, blk, 0, st, frames_dev, ws.labels, ws.slot_of, ws.bbox, ws.fg_count, ws.fg_list, ws.blabels);
+    pdl_launch(db_sort_components, n_frames, 256, 0, st, ws.n_comp, ws.roots, ws.order, ws.status, ws.ckey);
     size_t smem = db_candidate_smem_bytes(max_rh);
     {   // the opt-in belongs to the current device's copy of the kernel: one high-water mark per device
         static size_t configured[64] = {};
@@ -383,9 +495,9 @@ void launch_db_postprocess(const float* prob, const DetFrame* frames_dev, const 
         }
     }
     pdl_launch(db_candidates, dim3(16, n_frames), kCandThreads, smem, st, prob, frames_dev, ws.labels, ws.n_comp, ws.roots, ws.bbox,
-                                                                  ws.order, p, max_rh, ws.cand);
+                                                                  ws.order, p, max_rh, ws.cand, ws.blabels, ws.blk_listed, gx, gy);
     pdl_launch(db_compact, n_frames, 32, 0, st, ws.n_comp, ws.cand, p, ws.n_boxes, ws.quads, ws.scores, ws.status);
-    if (launches) *launches += 7;
+    if (launches) *launches += 8;
 }
 
 // the compaction alone, with p.max_boxes rows per frame (the candidates of the last launch_db_postprocess are reused)

@@ -9,7 +9,8 @@
 
 namespace vse {
 
-static constexpr int kSlotCap = 4096;   // connected components tracked per frame (more => error, never silent)
+static constexpr int kSlotCap = 4096;   // contours (components + hole borders) tracked per frame (more => error, never silent)
+static constexpr int kHoleFlag = 0x40000000;   // DbWorkspace::roots entry of a hole border: first hole pixel | kHoleFlag
 
 struct DetFrame {
     int map_off;   // first pixel of this frame's probability map in the det output value
@@ -33,6 +34,12 @@ struct DbWorkspace {
     int* order;       // [n_frames][kSlotCap] slots in cv2 contour order
     float* cand;      // [n_frames][max_candidates][10]: valid, score, quad[8]
     int* status;      // [n_frames] bit 0: too many components, bit 1: too many boxes, bit 2: non-finite probability
+    // hole borders (cv2.findContours RETR_LIST also reports them): background pixels of the listed blocks are labelled too
+    // (4-connectivity); a background component that never touches the image border or an unlisted block is a hole
+    int* blabels;     // [total map pixels] union-find over background pixels (valid inside listed blocks; -1 = foreground)
+    int* bopen;       // [total map pixels] at background roots: 1 = connected to the outside (not a hole)
+    int* blk_listed;  // [n_frames * blocks_y * blocks_x] 1 = block holds foreground (its blabels / bopen are valid)
+    int* ckey;        // [n_frames][kSlotCap] discovery key of a contour: 2 * start pixel (+ 1 for a hole border)
     int* fg_count;    // [1] number of (32 x 8)-pixel blocks that hold foreground
     int* fg_list;     // [n_frames * blocks_y * blocks_x] their codes (frame << 20 | block_y << 10 | block_x)
     // outputs

@@ -89,8 +89,10 @@ def load_library(path: Optional[str] = None):
 
 def bench_mode() -> dict:
     """Engine keyword arguments of the mode bench.py times (BASELINE configs[1]); tests/test_gpu_real_video.py holds exactly
-    this mode to the north-star bars (IoU >= 0.99 box-for-box, CER <= 1e-3) on the reference's sample videos."""
-    return dict(precision=PRECISION_FP16)
+    this mode to the north-star bars (IoU >= 0.99 box-for-box, CER <= 1e-3) on the reference's sample videos.  fp16
+    activation storage is ~1.5x faster but moves the 0.3 threshold crossing of the detector on ~1 % of real-video boxes
+    (tests/test_gpu_real_video.py reports it), so it is not the mode that is timed."""
+    return dict(precision=PRECISION_FP32_TC)
 
 
 def accurate_mode() -> dict:
