@@ -66,6 +66,11 @@ def parse_args():
         if args.video is None and os.path.exists(os.path.join(vids, "test_cn.mp4")):
             args.video = os.path.join(vids, "test_cn.mp4")
         args.frame_stride = 3
+    elif args.config == 3:
+        if "--steps" not in sys.argv:
+            args.steps = 1
+        if "--warmup" not in sys.argv:
+            args.warmup = 0
     elif args.config == 4:
         args.det, args.rec = args.det or "V4/ch_det", args.rec or "V4/ch_rec"
         args.batch, args.height, args.width, args.pool = 16, 2160, 3840, 2
@@ -511,6 +516,88 @@ def run_b200(args, rank, local_rank, world):
         emit(out)
 
 
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: four sample videos, fast mode, every video's schedule sharded over the ranks — whole jobs
+# --------------------------------------------------------------------------------------------------
+VIDEO_JOBS = [("test_en.mp4", "en", "V4/en_rec_fast", 97), ("test_cn.mp4", "ch", "V4/ch_rec_fast", 6625),
+              ("test_japan.mp4", "japan", "V3/japan_rec_fast", 4401), ("test_korean.flv", "korean", "V3/korean_rec_fast", 3690)]
+
+
+def run_videos(args, rank, local_rank, world):
+    """One step = the four videos through job.fast_mode_job (decoder thread -> pinned ring -> vse_prefetch / vse_run ->
+    raw.txt lines -> gather by frame -> de-dup -> .srt text on every rank).  Recognisers follow the reference's fallback chain
+    (backend/tools/paddle_model_config.py:73-82).  value = OCR'd frames of all videos / wall time of the slowest rank."""
+    import warnings
+    import torch
+    from video_subtitle_extractor_b200 import charset, engine as E, job, shard, weights
+    warnings.simplefilter("ignore", RuntimeWarning)       # dictionaries of ch / japan / korean are not in this image
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        torch.distributed.init_process_group("nccl", device_id=torch.device(dev))
+    vids = os.path.join(ROOT, "tests", "golden", "_videos")
+    jobs = [(os.path.join(vids, v), lang, rec, n) for v, lang, rec, n in VIDEO_JOBS if os.path.exists(os.path.join(vids, v)) and weights.have_plan(rec)]
+    if not jobs:
+        raise SystemExit("bench.py --config 3: tests/golden/_videos/ or the packed recogniser plans are missing")
+    eng = E.Engine(device=local_rank, **E.bench_mode())
+    eng.load_plan(E.PLAN_DET, weights.load_plan_blob("V4/ch_det_fast"), "V4/ch_det_fast")
+
+    def one_pass(stats):
+        n_frames, n_lines, n_subs = 0, 0, 0
+        for path, lang, rec, n_cls in jobs:
+            eng.load_plan(E.PLAN_REC, weights.load_plan_blob(rec), rec)
+            res = job.fast_mode_job(eng, path, charset.characters(lang, None, n_cls), rank=rank, world=world, batch=args.batch,
+                                    rec_char_type=lang, stats=stats)
+            n_frames += res.frames_ocr
+            n_lines += len(res.lines)
+            n_subs += len(res.subtitles)
+        return n_frames, n_lines, n_subs
+
+    for _ in range(args.warmup):
+        one_pass({})
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    stats = {}
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_frames, n_lines, n_subs = one_pass(stats)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    wall = time.perf_counter() - t0
+    wall_max = shard.max_over_ranks(wall, dev)
+    mine = (rank, n_frames, wall / args.steps, stats.get("feed_wait_s", 0) / args.steps, stats.get("engine_s", 0) / args.steps,
+            stats.get("frames_decoded", 0) // args.steps)
+    per_rank = [mine]
+    if world > 1:
+        bucket = [None] * world
+        torch.distributed.all_gather_object(bucket, mine)
+        per_rank = bucket
+    total = sum(r[1] for r in per_rank)
+    launches = eng.launch_count - l0
+    eng.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank == 0:
+        emit({"metric": METRIC, "value": total * args.steps / wall_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "f32", "data": "real video frames",
+              "config": {"workload": "BASELINE configs[3]: " + ", ".join(os.path.basename(j[0]) for j in jobs) + " in fast mode, whole jobs "
+                                     "(decode -> vse_run -> raw.txt -> de-dup -> .srt), each video's schedule sharded over the ranks",
+                         "baseline_config": 3, "frames_per_step": total, "raw_lines": n_lines, "subtitles": n_subs,
+                         "models": ["V4/ch_det_fast"] + [j[2] for j in jobs], "frames_per_vse_run": args.batch},
+              "e2e": {"value": total * args.steps / wall_max, "unit": UNIT, "note": "the job IS end to end: frames come from the "
+                      "video decoder through pinned host buffers, results go back to host text"},
+              "per_rank": [{"rank": r, "frames_ocr": n, "s_per_step": round(w, 3), "feed_wait_s": round(fw, 3), "engine_s": round(es, 3),
+                            "frames_decoded": fd} for r, n, w, fw, es, fd in per_rank],
+              "limiter": "video decode (one cv2 decoder thread per rank)" if mine[3] > mine[4] else "engine",
+              "gpu_launches": launches})
+
+
 _JSON_FD = None
 
 
@@ -547,6 +634,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.config == 3:
+        run_videos(args, rank, local_rank, world)
+        return
     run_b200(args, rank, local_rank, world)
 
 

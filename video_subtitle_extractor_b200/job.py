@@ -133,24 +133,40 @@ class FrameFeed:
             yield b
 
 
-def run_feed(engine, feed: FrameFeed, det_only: bool = False, mem_kind: Optional[int] = None) -> Dict[int, object]:
+def run_feed(engine, feed: FrameFeed, det_only: bool = False, mem_kind: Optional[int] = None,
+             stats: Optional[dict] = None) -> Dict[int, object]:
     """Every delivered frame through vse_run (det_only: vse_det_only) with one batch of look-ahead on the copy stream.
-    -> {frame number: engine.FrameResult}."""
+    -> {frame number: engine.FrameResult}.  stats (optional) accumulates seconds spent waiting for the decoder ('feed_wait_s')
+    and inside the engine calls ('engine_s') and the frames decoded / delivered."""
+    import time
     from . import engine as E
     mk = E.MEM_PINNED if mem_kind is None else mem_kind
     out: Dict[int, object] = {}
     it = iter(feed)
+    t_wait = t_eng = 0.0
+    t0 = time.perf_counter()
     cur = next(it, None)
+    t_wait += time.perf_counter() - t0
     while cur is not None:
+        t0 = time.perf_counter()
         nxt = next(it, None)                       # decoded (or being decoded) while the current batch computes
+        t1 = time.perf_counter()
         if nxt is not None:
             engine.prefetch(*feed.view(nxt)[:4], mem_kind=mk)
         ptrs, hs, ws, st = feed.view(cur)
         res = engine.run_device(ptrs, hs, ws, st, det_only=det_only, mem_kind=mk)
+        t2 = time.perf_counter()
+        t_wait += t1 - t0
+        t_eng += t2 - t1
         for no, r in zip(cur.numbers, res):
             out[no] = r
         feed.release(cur)
         cur = nxt
+    if stats is not None:
+        stats["feed_wait_s"] = stats.get("feed_wait_s", 0.0) + t_wait
+        stats["engine_s"] = stats.get("engine_s", 0.0) + t_eng
+        stats["frames_decoded"] = stats.get("frames_decoded", 0) + feed.frames_read
+        stats["frames_ocr"] = stats.get("frames_ocr", 0) + len(out)
     return out
 
 
@@ -182,7 +198,7 @@ class JobResult:
 def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, world: int = 1, batch: int = 32,
                   sub_area: Optional[Coordinate] = "default", rec_char_type: str = "en", drop_score: float = 0.75,
                   extract_frequency: int = 3, threshold: float = 0.8, half: Optional[str] = None, pinned: bool = True,
-                  write_srt: bool = True) -> JobResult:
+                  write_srt: bool = True, stats: Optional[dict] = None) -> JobResult:
     """Fast mode of the reference (`run` -> `extract_frame_by_fps`, backend/main.py:145-147) on this rank's share of the
     schedule.  `sub_area` 'default' = the reference's default area for the video's size; None = no area."""
     probe = FrameFeed(path, 1, 0, [], batch=1, slots=1, pinned=False)
@@ -194,7 +210,7 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
     results: Dict[int, object] = {}
     if mine:
         feed = FrameFeed(path, mine[0], mine[-1], mine, batch=batch, pinned=pinned, half=half)
-        results = run_feed(engine, feed)
+        results = run_feed(engine, feed, stats=stats)
     local = []
     for no in sorted(results):
         ls = rawtxt.lines_from_frame_result(no, results[no], characters, sub_area=sub_area, rec_char_type=rec_char_type,
@@ -209,7 +225,7 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
 def accurate_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, world: int = 1, batch: int = 64,
                       sub_area: Optional[Coordinate] = "default", rec_char_type: str = "ch", drop_score: float = 0.75,
                       threshold: float = 0.8, first: int = 1, last: Optional[int] = None, pinned: bool = True,
-                      write_srt: bool = True) -> JobResult:
+                      write_srt: bool = True, stats: Optional[dict] = None) -> JobResult:
     """Accurate mode of the reference (`extract_frame_by_det`, backend/main.py:255-376): the detector looks at EVERY frame and
     the recogniser reads the frames the controller asks for.  Here det + rec run over every frame of this rank's range in
     batches (`vse_run`), the records are gathered by frame number and the reference's decisions are replayed
@@ -225,7 +241,7 @@ def accurate_mode_job(engine, path: str, characters: Sequence[str], rank: int = 
     results: Dict[int, object] = {}
     if hi > lo:
         feed = FrameFeed(path, first + lo, first + hi - 1, None, batch=batch, pinned=pinned)
-        results = run_feed(engine, feed)
+        results = run_feed(engine, feed, stats=stats)
     local = [(no, ([q.tolist() for q in r.quads], [(ids_to_text(i, characters), float(s)) for i, s in zip(r.ids, r.rec_scores)]))
              for no, r in sorted(results.items())]
     merged = dict(shard.gather_by_frame(local))
