@@ -548,7 +548,7 @@ def run_videos(args, rank, local_rank, world):
         for path, lang, rec, n_cls in jobs:
             eng.load_plan(E.PLAN_REC, weights.load_plan_blob(rec), rec)
             res = job.fast_mode_job(eng, path, charset.characters(lang, None, n_cls), rank=rank, world=world, batch=args.batch,
-                                    rec_char_type=lang, stats=stats)
+                                    rec_char_type=lang, stats=stats, write_srt=rank == 0)
             n_frames += res.frames_ocr
             n_lines += len(res.lines)
             n_subs += len(res.subtitles)

@@ -51,7 +51,7 @@ void Engine::load_plan(int which, const void* blob, size_t n) {
     if (which < 0 || which > 1) throw InvalidArg{"plan index must be 0 (det) or 1 (rec)"};
     LoadedPlan& lp = plans_[which];
     lp.loaded = false;
-    last_tab_[which].clear();
+    purge_contexts(which);
     std::string err = lp.data.parse(blob, n);
     if (!err.empty()) throw InvalidArg{err};
     // activation type of this plan: the engine's, except that VSE_FLAG_DET_FP32 keeps the detector in fp32 (server detector
@@ -79,7 +79,13 @@ void Engine::set_conv_input_ranges(int which, const float* absmax, int n_steps) 
         }
         lp.a_scale[k] = s;
     }
-    last_tab_[which].clear();                                // contexts cache the scale: rebuild on the next run
+    purge_contexts(which);                                   // contexts cache the scale: rebuild on the next run
+}
+
+void Engine::purge_contexts(int which) {
+    last_tab_[which].clear();
+    for (auto& sl : ctx_store_[which]) { sl.cx.tabs.release(); sl.cx.tc_gdev.release(); }
+    ctx_store_[which].clear();
 }
 
 void Engine::prepare_plan(int which, LoadedPlan& lp) {
@@ -580,6 +586,16 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         if (!why.empty()) cx.tc[k].valid = false;
         cx.tc[k].a_scale = lp.a_scale[k];
     }
+    // device tables of the ragged steps (one launch per step: launch_conv_tc_groups)
+    cx.tc_goff.assign(pd.steps.size(), 0);
+    cx.tc_gup.assign(pd.steps.size(), 0);
+    size_t gbytes = 0;
+    for (size_t k = 0; k < pd.steps.size(); k++)
+        if (!cx.tc_groups[k].empty()) {
+            cx.tc_goff[k] = gbytes;
+            gbytes += (tc_groups_dev_bytes(int(cx.tc_groups[k].size())) + 255) & ~size_t(255);
+        }
+    if (gbytes) cx.tc_gdev.reserve(gbytes);
 }
 
 void* Engine::vptr(int which, int vid) const {
@@ -608,12 +624,52 @@ const void* Engine::value_ptr(int which, int vid, int* cs, const Geo** geo) {
 void Engine::run_plan(int which, const std::vector<ImgTab>& in_tab, const uint8_t* input_dev, bool keep_all) {
     // geometry + arena plan are reused when the batch has the same shapes as the previous call (the usual case for
     // the detector: every frame of a video resizes to the same map)
-    bool same = plans_[which].loaded && last_keep_all_[which] == keep_all && last_tab_[which].size() == in_tab.size();
-    for (size_t i = 0; same && i < in_tab.size(); i++)
-        same = last_tab_[which][i].h == in_tab[i].h && last_tab_[which][i].w == in_tab[i].w && last_tab_[which][i].vw == in_tab[i].vw;
-    if (!same) {
+    auto same_tab = [&](const std::vector<ImgTab>& t, bool ka) {
+        bool same = ka == keep_all && t.size() == in_tab.size() && !t.empty();
+        for (size_t i = 0; same && i < in_tab.size(); i++) same = t[i].h == in_tab[i].h && t[i].w == in_tab[i].w && t[i].vw == in_tab[i].vw;
+        return same;
+    };
+    if (!(plans_[which].loaded && same_tab(last_tab_[which], last_keep_all_[which]))) {
+        static const int kCtxCache = [] { const char* e = getenv("VSE_CTX_CACHE"); return e ? atoi(e) : 6; }();
+        auto& store = ctx_store_[which];
+        // park the active context, then look for a parked one with this geometry
+        if (!last_tab_[which].empty() && kCtxCache > 0) {
+            CtxSlot sl;
+            sl.cx = std::move(ctx_[which]);
+            sl.tab = std::move(last_tab_[which]);
+            sl.keep_all = last_keep_all_[which];
+            sl.stamp = ++ctx_clock_;
+            store.push_back(std::move(sl));
+            ctx_[which] = ExecContext{};
+        } else {
+            ctx_[which].tabs.release();
+            ctx_[which].tc_gdev.release();
+            ctx_[which] = ExecContext{};
+        }
         last_tab_[which].clear();
-        build_context(which, in_tab, keep_all);
+        int hit = -1;
+        for (size_t i = 0; i < store.size() && hit < 0; i++)
+            if (same_tab(store[i].tab, store[i].keep_all)) hit = int(i);
+        if (hit >= 0) {
+            ctx_[which] = std::move(store[hit].cx);
+            store.erase(store.begin() + hit);
+        } else {
+            while (int(store.size()) >= std::max(kCtxCache, 1)) {       // evict the least recently used geometry
+                size_t old = 0;
+                for (size_t i = 1; i < store.size(); i++)
+                    if (store[i].stamp < store[old].stamp) old = i;
+                store[old].cx.tabs.release();
+                store[old].cx.tc_gdev.release();
+                store.erase(store.begin() + old);
+            }
+            const void* arena_before = arena_[which].p;
+            build_context(which, in_tab, keep_all);
+            if (arena_[which].p != arena_before) {
+                // the arena moved (it only ever grows): parked contexts hold tensor maps into the old allocation
+                for (auto& sl : store) { sl.cx.tabs.release(); sl.cx.tc_gdev.release(); }
+                store.clear();
+            }
+        }
         last_tab_[which] = in_tab;
         last_keep_all_[which] = keep_all;
     }
@@ -996,24 +1052,26 @@ bool Engine::launch_conv(int which, int step, const ConvArgs& a, int prec) {
     auto& groups = ctx_[which].tc_groups[step];
     if (!groups.empty()) {   // ragged KxK convolution: one tensor-core launch per run of equal-sized images
         const size_t es = plan_prec_[which] == VSE_PRECISION_FP16 ? 2 : 4;
-        bool ok = true;
-        size_t done = 0;
+        ExecContext& cx = ctx_[which];
+        std::vector<TcConv*> gp;
+        std::vector<long long> off;
         for (auto& g : groups) {
             TcConv& tg = g.tc;
             tg.out = static_cast<char*>(a.out) + size_t(g.pix_off) * a.out_cs * es;   // same-padding stride 1: output pixels = input pixels
             tg.out_cs = a.out_cs;
             tg.n_store = a.cout_store;
-            tg.epi = a.epi;
-            if (a.epi.res) tg.epi.res = static_cast<const char*>(a.epi.res) + size_t(g.pix_off) * a.epi.res_cs * es;
-            if (!launch_conv_tc(tg, sm_count, stream).empty()) { ok = false; break; }
-            done++;
+            tg.epi = a.epi;       // residual: the value's base pointer — the kernel adds the group's pixel offset
+            gp.push_back(&tg);
+            off.push_back(g.pix_off);
         }
-        if (ok) {
-            tc_launches += int64_t(groups.size());
-            launches += int64_t(groups.size()) - 1;
+        bool up = cx.tc_gup[step] != 0;
+        const std::string err = launch_conv_tc_groups(gp.data(), off.data(), int(gp.size()), static_cast<char*>(cx.tc_gdev.p) + cx.tc_goff[step],
+                                                      &up, sm_count, stream);
+        cx.tc_gup[step] = up ? 1 : 0;
+        if (err.empty()) {
+            tc_launches++;
             return true;
         }
-        if (done > 0) throw StateError{"ragged tensor-core convolution failed after launching part of its groups"};
         groups.clear();   // e.g. an output view the TMA store cannot address: CUDA-core kernel from now on
     }
     (void)prec;

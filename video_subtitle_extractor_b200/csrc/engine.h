@@ -142,6 +142,9 @@ struct ExecContext {
         int64_t pix_off = 0;   // first pixel of the group in the step's input / output / residual values
     };
     std::vector<std::vector<TcGroup>> tc_groups;
+    DevBuf tc_gdev;                 // per ragged step: the groups' tensor maps + geometry table on the device (gemm_tc.h)
+    std::vector<size_t> tc_goff;    // byte offset of a step's table in tc_gdev
+    std::vector<char> tc_gup;       // 1 = the table on the device is current
     std::vector<char> se_conv; // per step: 1 = 1x1 conv heading a fused residual squeeze-excite group (build_context)
     std::vector<int> kind;    // per step, filled by exec_steps: which kernel family ran (see Engine::time_steps)
 };
@@ -206,6 +209,18 @@ class Engine {
     Pipeline* pipe_ = nullptr;
     std::vector<ImgTab> last_tab_[2];
     bool last_keep_all_[2] = {false, false};
+    // Contexts of recent batch geometries (per plan).  A subtitle stays on screen for dozens of frames, so consecutive batches
+    // of a video repeat a small set of recogniser geometries (same boxes -> same padded crop widths): shape inference, arena
+    // plan and ~100 tensor-map encodings are reused instead of rebuilt between the detector's and the recogniser's kernels.
+    struct CtxSlot {
+        ExecContext cx;
+        std::vector<ImgTab> tab;
+        bool keep_all = false;
+        uint64_t stamp = 0;
+    };
+    std::vector<CtxSlot> ctx_store_[2];
+    uint64_t ctx_clock_ = 0;
+    void purge_contexts(int which);
 };
 
 }  // namespace vse

@@ -55,6 +55,11 @@ struct TcParams {
     int gate_c, gate_rows;
     float a_scale;     // split mode: operand rows are multiplied by this power of two before the fp16 split (see transform warps)
     float acc_scale;   // accumulator -> output units (1 / (a_scale * weight scale); 1 outside split mode)
+    // ragged batches (recogniser crops of different widths): several groups of equal-sized images in ONE launch; group g has
+    // its own activation / output tensor maps (gmaps[2g], gmaps[2g + 1], device memory) and geometry (gtab[g])
+    const CUtensorMap* gmaps;
+    const TcGroupDev* gtab;
+    int n_groups;
     int n_total;       // n_chunks * n_chunk (bias / post arrays are readable up to here)
     int param_smem;    // 1: bias/scale/shift staged in shared memory
 };
@@ -275,6 +280,37 @@ __device__ __forceinline__ float tc_act(float x, int act, float slope, float off
     }
 }
 
+// geometry of the group a tile belongs to (ragged launches); tiles come in increasing order per CTA, so the search resumes
+// where it stopped.  A group's tensor maps live in global memory and are rewritten by an upload kernel for every new batch
+// geometry: the thread that hands them to TMA acquires them through the tensormap proxy first.
+struct TileGeo {
+    const CUtensorMap* ma;
+    const CUtensorMap* mo;
+    int H, W, tiles_x, tiles_y, m_local, g;
+    long long pix_off;
+};
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap* m) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tile_geo(const TcParams& p, const CUtensorMap* ma0, const CUtensorMap* mo0, int m_tile, TileGeo& c,
+                                         bool acquire_a, bool acquire_o) {
+    if (p.n_groups == 0) {
+        c.ma = ma0; c.mo = mo0; c.H = p.H; c.W = p.W; c.tiles_x = p.tiles_x; c.tiles_y = p.tiles_y; c.m_local = m_tile; c.pix_off = 0;
+        return;
+    }
+    int g = c.g < 0 ? 0 : c.g;
+    while (g + 1 < p.n_groups && m_tile >= p.gtab[g + 1].tile_begin) g++;
+    if (g != c.g) {
+        c.g = g;
+        const TcGroupDev t = p.gtab[g];
+        c.ma = p.gmaps + 2 * g; c.mo = p.gmaps + 2 * g + 1;
+        c.H = t.H; c.W = t.W; c.tiles_x = t.tiles_x; c.tiles_y = t.tiles_y; c.pix_off = t.pix_off;
+        if (acquire_a) tensormap_acquire(c.ma);
+        if (acquire_o) tensormap_acquire(c.mo);
+    }
+    c.m_local = m_tile - p.gtab[g].tile_begin;
+}
+
 // ------------------------------------------------------------------------------------------------
 // epilogue: 8 warps.  Warp w may only touch TMEM lanes [32 * (w % 4), +32) (hardware rule), so q = w % 4 picks the
 // 32 output pixels (one per lane) and `half` splits the accumulator columns in 32-column pairs between the two warps
@@ -394,18 +430,21 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
     const int out_bufs = p.out_bufs;
     int acc = 0, slot = 0;
     uint32_t acc_phase = 0;
+    TileGeo tg;
+    tg.g = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
         long long pix = -1;
         int img = 0, y0 = 0, x0 = 0;
         if (p.spatial) {
-            const int per_img = p.tiles_x * p.tiles_y;
-            img = m_tile / per_img;
-            const int r = m_tile - img * per_img;
-            y0 = (r / p.tiles_x) * (p.halo ? 16 : 8);
-            x0 = (r % p.tiles_x) * (p.halo ? 8 : 16);
+            tile_geo(p, nullptr, map_o, m_tile, tg, false, issuer);
+            const int per_img = tg.tiles_x * tg.tiles_y;
+            img = tg.m_local / per_img;
+            const int r = tg.m_local - img * per_img;
+            y0 = (r / tg.tiles_x) * (p.halo ? 16 : 8);
+            x0 = (r % tg.tiles_x) * (p.halo ? 8 : 16);
             const int y = y0 + (p.halo ? row >> 3 : row >> 4), x = x0 + (p.halo ? row & 7 : row & 15);
-            if (y < p.H && x < p.W) pix = (long long)img * p.H * p.W + (long long)y * p.W + x;
+            if (y < tg.H && x < tg.W) pix = tg.pix_off + (long long)img * tg.H * tg.W + (long long)y * tg.W + x;
         } else {
             const long long m = (long long)m_tile * BLOCK_M + row;
             if (m < p.M) pix = m;
@@ -450,7 +489,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
             epi_barrier();
             if (issuer) {
                 const void* src = sout + size_t(slot) * kOutBufBytes;
-                if (p.spatial) tma_store_4d(map_o, src, ch0 + sub * SUBC, x0, y0, img);
+                if (p.spatial) tma_store_4d(tg.mo, src, ch0 + sub * SUBC, x0, y0, img);
                 else tma_store_2d(map_o, src, ch0 + sub * SUBC, m_tile * BLOCK_M);
                 tma_store_commit();
                 // the tile written two barriers from now is free again (see ring note); shorter rings wait for more stores
@@ -693,15 +732,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // ---------------- TMA producer ----------------
             int stage = 0;
             uint32_t phase = 0;
+            TileGeo tg;
+            tg.g = -1;
+            tg.ma = &map_a;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_chunks, n_idx = tile - m_tile * p.n_chunks;
                 int img = 0, y0 = 0, x0 = 0;
                 if (p.spatial) {
-                    const int per_img = p.tiles_x * p.tiles_y;
-                    img = m_tile / per_img;
-                    const int r = m_tile - img * per_img;
-                    y0 = (r / p.tiles_x) * (p.halo ? 16 : 8);
-                    x0 = (r % p.tiles_x) * (p.halo ? 8 : 16);
+                    tile_geo(p, &map_a, nullptr, m_tile, tg, true, false);
+                    const int per_img = tg.tiles_x * tg.tiles_y;
+                    img = tg.m_local / per_img;
+                    const int r = tg.m_local - img * per_img;
+                    y0 = (r / tg.tiles_x) * (p.halo ? 16 : 8);
+                    x0 = (r % tg.tiles_x) * (p.halo ? 8 : 16);
                 }
                 for (int it = 0; it < k_iters; it++) {
                     const int tap = it / p.num_kb, kb = it - tap * p.num_kb;   // rowbox: tap = kx
@@ -709,19 +752,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_expect_tx(&full[stage], uint32_t(p.a_tx + b_bytes));
                     uint8_t* a_dst = smem + size_t(stage) * stage_bytes;
                     if (p.halo) {
-                        tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 - p.pw, y0 - p.ph, img);
+                        tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 - p.pw, y0 - p.ph, img);
                         for (int tp = 0; tp < taps && !p.b_resident; tp++)
                             tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * p.kbb,
                                         n_idx * p.n_chunk);
                     } else if (p.rowbox) {
-                        tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 + tap - p.pw, y0 - p.ph, img);
+                        tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 + tap - p.pw, y0 - p.ph, img);
                         for (int ky = 0; ky < p.kh && !p.b_resident; ky++)
                             tma_load_2d(a_dst + p.a_bytes + ky * p.n_chunk * 128, &map_b, &full[stage],
                                         (ky * p.kw + tap) * p.k_pad + kb * p.kbb, n_idx * p.n_chunk);
                     } else {
                         if (p.spatial) {
                             const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                            tma_load_4d(a_dst, &map_a, &full[stage], kb * p.kb_elems, x0 + kx - p.pw, y0 + ky - p.ph, img);
+                            tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 + kx - p.pw, y0 + ky - p.ph, img);
                         } else {
                             tma_load_2d(a_dst, &map_a, &full[stage], kb * p.kb_elems, m_tile * BLOCK_M);
                         }
@@ -1018,8 +1061,9 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
 }
 
 // output tensor map (TMA stores): [n_store channels] x pixels, row pitch out_cs; re-encoded only when the target changes
-static std::string tc_output_map(TcConv& t) {
+static std::string tc_output_map(TcConv& t, bool* changed = nullptr) {
     if (t.map_o_ptr == t.out && t.map_o_cs == t.out_cs && t.map_o_n == t.n_store) return "";
+    if (changed) *changed = true;
     std::string err;
     const int es = (t.tf32 || t.split) ? 4 : 2;
     const cuuint32_t cols = cuuint32_t(128 / es);   // one staging row = 64 fp16 or 32 fp32 columns
@@ -1038,6 +1082,9 @@ static std::string tc_output_map(TcConv& t) {
     return err;
 }
 
+static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const CUtensorMap* gmaps, const TcGroupDev* gtab,
+                               int n_groups, int total_m_tiles);
+
 std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     const bool of32 = t.tf32 || t.split;
     if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (of32 ? 3 : 7))) return "output view not 16-byte aligned";
@@ -1045,10 +1092,58 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
         std::string err = tc_output_map(t);
         if (!err.empty()) return err;
     }
+    return launch_impl(t, sm_count, st, nullptr, nullptr, 0, t.num_m_tiles);
+}
+
+// Ragged batch: the groups (runs of equal-sized images, each with its own tensor maps) of one KxK convolution in ONE launch.
+// `dev` receives [2 maps per group][TcGroupDev per group] (tc_groups_dev_bytes(n) bytes, 128-byte aligned); `uploaded` caches
+// that the table on the device is current (same context, same output views).
+size_t tc_groups_dev_bytes(int n_groups) { return size_t(n_groups) * (2 * sizeof(CUtensorMap) + sizeof(TcGroupDev)) + 256; }
+
+std::string launch_conv_tc_groups(TcConv* const* gs, const long long* pix_off, int n_groups, void* dev, bool* uploaded, int sm_count,
+                                  cudaStream_t st) {
+    if (n_groups <= 0) return "no groups";
+    const bool of32 = gs[0]->tf32 || gs[0]->split;
+    bool changed = !*uploaded;
+    for (int g = 0; g < n_groups; g++) {
+        TcConv& t = *gs[g];
+        if (!t.spatial || t.halo != gs[0]->halo || t.rowbox != gs[0]->rowbox || t.b_resident != gs[0]->b_resident || t.num_kb != gs[0]->num_kb)
+            return "groups with different kernel shapes";
+        if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (of32 ? 3 : 7))) return "output view not 16-byte aligned";
+        std::string err = tc_output_map(t, &changed);
+        if (!err.empty()) return err;
+    }
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    const size_t map_bytes = size_t(n_groups) * 2 * sizeof(CUtensorMap);
+    int tiles = 0;
+    if (changed) {
+        std::vector<unsigned char> host(map_bytes + size_t(n_groups) * sizeof(TcGroupDev));
+        for (int g = 0; g < n_groups; g++) {
+            const TcConv& t = *gs[g];
+            std::memcpy(host.data() + size_t(2 * g) * sizeof(CUtensorMap), &t.map_a, sizeof(CUtensorMap));
+            std::memcpy(host.data() + size_t(2 * g + 1) * sizeof(CUtensorMap), &t.map_o, sizeof(CUtensorMap));
+            TcGroupDev d{tiles, t.n_img, t.H, t.W, t.tiles_x, t.tiles_y, pix_off[g]};
+            std::memcpy(host.data() + map_bytes + size_t(g) * sizeof(TcGroupDev), &d, sizeof(d));
+            tiles += t.num_m_tiles;
+        }
+        launch_upload(dev, host.data(), host.size(), st);
+        *uploaded = true;
+    } else {
+        for (int g = 0; g < n_groups; g++) tiles += gs[g]->num_m_tiles;
+    }
+    const CUtensorMap* gmaps = static_cast<const CUtensorMap*>(dev);
+    const TcGroupDev* gtab = reinterpret_cast<const TcGroupDev*>(static_cast<const char*>(dev) + map_bytes);
+    return launch_impl(*gs[0], sm_count, st, gmaps, gtab, n_groups, tiles);
+}
+
+static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const CUtensorMap* gmaps, const TcGroupDev* gtab,
+                               int n_groups, int total_m_tiles) {
+    const bool of32 = t.tf32 || t.split;
     TcParams p{};
+    p.gmaps = gmaps; p.gtab = gtab; p.n_groups = n_groups;
     p.spatial = t.spatial; p.M = t.M; p.n_img = t.n_img; p.H = t.H; p.W = t.W; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
     p.kh = t.kh; p.kw = t.kw; p.ph = t.ph; p.pw = t.pw; p.num_kb = t.num_kb; p.k_pad = t.k_pad;
-    p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = t.num_m_tiles;
+    p.n_chunk = t.n_chunk; p.n_chunks = t.n_chunks; p.n_store = t.n_store; p.num_m_tiles = total_m_tiles;
     p.cin = t.cin;
     p.tf32 = t.tf32;
     p.split = t.split;
@@ -1096,7 +1191,7 @@ std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
         cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    const int total = t.num_m_tiles * t.n_chunks;
+    const int total = total_m_tiles * t.n_chunks;
     const int grid = std::max(1, std::min(total, sm_count));
     if (t.split) pdl_launch(conv_tc_kernel<true>, grid, kThreads, smem, st, t.map_a, t.map_b, t.map_o, p);
     else pdl_launch(conv_tc_kernel<false>, grid, kThreadsBase, smem, st, t.map_a, t.map_b, t.map_o, p);

@@ -73,4 +73,16 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
 // returns an empty string on success, else why the launch was not possible (nothing launched)
 std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st);
 
+// one group of a ragged launch as the kernel reads it
+struct TcGroupDev {
+    int tile_begin, n_img, H, W, tiles_x, tiles_y;
+    long long pix_off;      // first pixel of the group inside the step's values (residual addressing)
+};
+// Ragged batch (recogniser crops of different padded widths): every group (run of equal-sized images; each TcConv set up by
+// tc_conv_setup on its own slice, out / epi filled) of one KxK convolution in ONE launch.  `dev`: tc_groups_dev_bytes(n) bytes
+// of device memory owned by the caller for the lifetime of the context; *uploaded: the table there is current.
+size_t tc_groups_dev_bytes(int n_groups);
+std::string launch_conv_tc_groups(TcConv* const* groups, const long long* pix_off, int n_groups, void* dev, bool* uploaded,
+                                  int sm_count, cudaStream_t st);
+
 }  // namespace vse

@@ -51,6 +51,8 @@ Engine::~Engine() {
     for (int i = 0; i < 2; i++) {
         plans_[i].weights.release();
         ctx_[i].tabs.release();
+        ctx_[i].tc_gdev.release();
+        for (auto& sl : ctx_store_[i]) { sl.cx.tabs.release(); sl.cx.tc_gdev.release(); }
         arena_[i].release();
     }
     dbg_.release();

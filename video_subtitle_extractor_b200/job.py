@@ -74,6 +74,7 @@ class FrameFeed:
             self._free.put(s)
         self._ready: "queue.Queue[Optional[Batch]]" = queue.Queue()
         self.frames_read = 0
+        self.msec: Dict[int, float] = {}          # decoder timestamp after reading frame `no` (what the SRT writer asks for)
         self._err: Optional[BaseException] = None
         self._thread = threading.Thread(target=self._decode, daemon=True)
         self._thread.start()
@@ -89,13 +90,16 @@ class FrameFeed:
             no = self.first - 1
             cur: Optional[Batch] = None
             while no < stop:
-                ok, frame = cap.read()
-                if not ok:
+                if not cap.grab():                 # frames that are not OCR tasks are decoded but never converted / copied
                     break
                 no += 1
                 self.frames_read += 1
+                self.msec[no] = cap.get(cv2.CAP_PROP_POS_MSEC)
                 if want is not None and no not in want:
                     continue
+                ok, frame = cap.retrieve()
+                if not ok:
+                    break
                 if cur is None:
                     s = self._free.get()
                     cur = Batch([], s, self.slots[s])
@@ -170,19 +174,34 @@ def run_feed(engine, feed: FrameFeed, det_only: bool = False, mem_kind: Optional
     return out
 
 
-def _srt(lines: List[str], fps: float, path: str, threshold: float) -> Tuple[List[Tuple[str, str, str]], str]:
+def _srt(lines: List[str], fps: float, path: str, threshold: float,
+         msec: Optional[Dict[int, float]] = None) -> Tuple[List[Tuple[str, str, str]], str]:
+    """`msec`: timestamps the feed recorded while decoding ({1-based frame number: POS_MSEC after reading it}).  The reference
+    seeks and reads once per subtitle boundary (`_frame_to_timecode`, backend/main.py:738-742: POS_FRAMES = n, read, POS_MSEC);
+    that is the timestamp after reading frame n + 1, which the sequential decode has already seen — identical values, no seek.
+    Frames the feed did not decode fall back to the reference's seek."""
     import cv2
     subs = dedup.remove_duplicates(lines, threshold, use_vsf=False)
-    cap = cv2.VideoCapture(path)
+    cap = [None]
 
-    def pos_msec(frame_no):                        # the decoder calls of _frame_to_timecode (reference backend/main.py:738-742)
-        cap.set(cv2.CAP_PROP_POS_FRAMES, frame_no)
-        ok, _ = cap.read()
-        return cap.get(cv2.CAP_PROP_POS_MSEC) if ok else None
+    def pos_msec(frame_no):
+        if msec is not None and frame_no + 1 in msec:
+            return msec[frame_no + 1]
+        if cap[0] is None:
+            cap[0] = cv2.VideoCapture(path)
+        cap[0].set(cv2.CAP_PROP_POS_FRAMES, frame_no)
+        ok, _ = cap[0].read()
+        return cap[0].get(cv2.CAP_PROP_POS_MSEC) if ok else None
 
     text, _ = dedup.srt_text(subs, fps, pos_msec)
-    cap.release()
+    if cap[0] is not None:
+        cap[0].release()
     return subs, text
+
+
+def _gather_msec(feed: Optional["FrameFeed"]) -> Dict[int, float]:
+    local = sorted(feed.msec.items()) if feed is not None else []
+    return dict(shard.gather_by_frame(local))
 
 
 @dataclass
@@ -208,6 +227,7 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
     if sub_area == "default":
         sub_area = default_sub_area(probe.h, probe.w)
     results: Dict[int, object] = {}
+    feed = None
     if mine:
         feed = FrameFeed(path, mine[0], mine[-1], mine, batch=batch, pinned=pinned, half=half)
         results = run_feed(engine, feed, stats=stats)
@@ -218,7 +238,8 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
         local.append((no, ls))
     merged = shard.gather_by_frame(local)
     lines = [l for _, ls in merged for l in ls]
-    subs, text = _srt(lines, probe.fps, path, threshold) if write_srt else ([], "")
+    msec = _gather_msec(feed)
+    subs, text = _srt(lines, probe.fps, path, threshold, msec) if write_srt else ([], "")
     return JobResult(lines, subs, text, len(results), sorted(results), results)
 
 
@@ -239,6 +260,7 @@ def accurate_mode_job(engine, path: str, characters: Sequence[str], rank: int = 
     if sub_area == "default":
         sub_area = default_sub_area(probe.h, probe.w)
     results: Dict[int, object] = {}
+    feed = None
     if hi > lo:
         feed = FrameFeed(path, first + lo, first + hi - 1, None, batch=batch, pinned=pinned)
         results = run_feed(engine, feed, stats=stats)
@@ -260,7 +282,8 @@ def accurate_mode_job(engine, path: str, characters: Sequence[str], rank: int = 
         if dt_box is None:                        # the worker runs predict on the task's own frame (subtitle_ocr.py:29-30)
             dt_box, rec = predict(k)
         lines += rawtxt.frame_lines(first + k - 1, dt_box, rec, sub_area=sub_area, rec_char_type=rec_char_type, drop_score=drop_score)
-    subs, text = _srt(lines, probe.fps, path, threshold) if write_srt else ([], "")
+    msec = _gather_msec(feed)
+    subs, text = _srt(lines, probe.fps, path, threshold, msec) if write_srt else ([], "")
     res = JobResult(lines, subs, text, len(results), sorted(results), results)
     res.tasks = tasks
     return res
