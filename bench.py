@@ -280,7 +280,7 @@ def step_roofline(eng, E):
                 dw_fast = {"0": "dwconv_fast_kernel", "1": "dwconv_tile_kernel"}.get(os.environ.get("VSE_DW_MODE", "2"), "dwconv_reg_kernel")
                 kname = dw_fast if kind == 2 else "dwconv_kernel"
             elif op == P.OP_DECONV2:
-                kname = "db_head_fused_kernel" if kind == 2 else "deconv2_kernel"
+                kname = "db_head_fused_kernel" if kind == 2 else ("conv_tc_kernel" if kind == 1 else "deconv2_kernel")
             elif op == P.OP_LSTM:
                 kname = "lstm_recurrent_kernel"
             else:

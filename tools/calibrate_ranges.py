@@ -54,7 +54,7 @@ def synth_frames():
 
 def record(pl, env, mx):
     for k, s in enumerate(pl.steps):
-        if s.op == P.OP_CONV and s.ins[0] in env:
+        if s.op in (P.OP_CONV, P.OP_DECONV2) and s.ins[0] in env:
             mx[k] = max(mx.get(k, 0.0), float(env[s.ins[0]].abs().max()))
 
 

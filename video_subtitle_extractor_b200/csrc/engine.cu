@@ -236,6 +236,8 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
     lp.tcw_off.assign(pd.steps.size(), 0);
     lp.tcw_pk.assign(pd.steps.size(), TcWeights{});
     lp.tcw_pk_off.assign(pd.steps.size(), 0);
+    lp.tcw_dc.assign(pd.steps.size() * 4, TcWeights{});
+    lp.tcw_dc_off.assign(pd.steps.size() * 4, 0);
     if (plan_prec_[which] != VSE_PRECISION_FP32 && !(cfg.flags & VSE_FLAG_NO_TENSOR_CORES)) {
         const int tc_mode = plan_prec_[which] == VSE_PRECISION_TF32 ? TC_TF32 : plan_prec_[which] == VSE_PRECISION_FP32_TC ? TC_SPLIT : TC_F16;
         std::vector<uint16_t> all;
@@ -247,8 +249,18 @@ void Engine::prepare_plan(int which, LoadedPlan& lp) {
             t.b.shrink_to_fit();
             return off;
         };
+        lp.tcw_dc.assign(pd.steps.size() * 4, TcWeights{});
+        lp.tcw_dc_off.assign(pd.steps.size() * 4, 0);
         for (size_t k = 0; k < pd.steps.size(); k++) {
             const StepRec& s = pd.steps[k];
+            if (s.op == OP_DECONV2 && s.p[P_COUT] % 8 == 0 && pd.values[s.out].dtype != DT_F32 && s.ins[0] != pd.hdr.input_vid) {
+                const int cin = s.p[P_CIN], cout = s.p[P_COUT];
+                for (int pos = 0; pos < 4; pos++) {     // canonical layout [kh][kw][cout][cin]: position pos = dy * 2 + dx
+                    lp.tcw_dc[k * 4 + pos] = tc_pack_weights(pd.w(s, W_WEIGHT) + size_t(pos) * cout * cin, cout, cin, 1, tc_mode);
+                    lp.tcw_dc_off[k * 4 + pos] = append(lp.tcw_dc[k * 4 + pos]);
+                }
+                continue;
+            }
             if (s.op != OP_CONV || s.p[P_SH] != 1 || s.p[P_SW] != 1) continue;
             lp.tcw[k] = tc_pack_weights(pd.w(s, W_WEIGHT), s.p[P_COUT], s.p[P_CIN], s.p[P_KH] * s.p[P_KW], tc_mode);
             lp.tcw_off[k] = append(lp.tcw[k]);
@@ -586,6 +598,26 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         if (!why.empty()) cx.tc[k].valid = false;
         cx.tc[k].a_scale = lp.a_scale[k];
     }
+    // transposed convolutions: four spatial 1x1 launches over the (uniform) input geometry
+    cx.tc_dc.assign(pd.steps.size() * 4, TcConv{});
+    for (size_t k = 0; k < pd.steps.size(); k++) {
+        const StepRec& s = pd.steps[k];
+        if (s.op != OP_DECONV2 || lp.tcw_dc[k * 4].n_chunk == 0) continue;
+        const Geo& gi = cx.geos[cx.vals[s.ins[0]].geo];
+        bool uniform = true;
+        for (auto& t : gi.tab) uniform = uniform && t.h == gi.tab[0].h && t.w == gi.tab[0].w;
+        if (!uniform) continue;
+        bool ok = true;
+        for (int pos = 0; pos < 4 && ok; pos++) {
+            TcConv& t = cx.tc_dc[k * 4 + pos];
+            const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_dc_off[k * 4 + pos];
+            ok = tc_conv_setup(t, vptr(which, s.ins[0]), value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw_dc[k * 4 + pos], false, gi.total,
+                               cx.n_img, gi.tab[0].h, gi.tab[0].w, 1, 1, 0, 0, false, false).empty();
+            t.a_scale = lp.a_scale[k];
+        }
+        if (!ok)
+            for (int pos = 0; pos < 4; pos++) cx.tc_dc[k * 4 + pos].valid = false;
+    }
     // device tables of the ragged steps (one launch per step: launch_conv_tc_groups)
     cx.tc_goff.assign(pd.steps.size(), 0);
     cx.tc_gup.assign(pd.steps.size(), 0);
@@ -822,7 +854,36 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                         cx.kind[k] = 3;
                         if (step_events) cudaEventRecord((*step_events)[k], stream);
                     } else {
-                        launch_deconv2(a, s.p[P_COUT], prec, stream);
+                        bool on_tc = cx.tc_dc[k * 4].valid && !a.epi.res;
+                        if (on_tc) {
+                            // out[2y + dy][2x + dx] = act(W[dy][dx] x[y][x] + b): four 1x1 convolutions whose outputs interleave
+                            const Geo& go = geo_of(s.out);
+                            const int wo = go.tab[0].w, ho = go.tab[0].h;
+                            const size_t es = prec == 0 ? 2 : 4;
+                            for (int pos = 0; pos < 4 && on_tc; pos++) {
+                                TcConv& t = cx.tc_dc[k * 4 + pos];
+                                const int dy = pos >> 1, dx = pos & 1;
+                                t.out = static_cast<char*>(a.out) + (size_t(dy) * wo + dx) * a.out_cs * es;
+                                t.out_cs = a.out_cs;
+                                t.n_store = a.cout_store;
+                                t.o_px = 2LL * a.out_cs;
+                                t.o_row = 2LL * wo * a.out_cs;
+                                t.o_img = (long long)ho * wo * a.out_cs;
+                                t.epi = a.epi;
+                                if (!launch_conv_tc(t, sm_count, stream).empty()) {
+                                    if (pos > 0) throw StateError{"transposed convolution failed after launching part of its positions"};
+                                    on_tc = false;
+                                }
+                            }
+                            if (on_tc) {
+                                tc_launches += 4;
+                                launches += 3;
+                                cx.kind[k] = 1;
+                            } else {
+                                for (int pos = 0; pos < 4; pos++) cx.tc_dc[k * 4 + pos].valid = false;
+                            }
+                        }
+                        if (!on_tc) launch_deconv2(a, s.p[P_COUT], prec, stream);
                     }
                 } else if (s.op == OP_STEM && fast && !(cfg.flags & VSE_FLAG_NO_FAST_STEM) && launch_stem_fast(a, s.p[P_COUT], max_units(2), stream, prec)) {
                     cx.kind[k] = 2;

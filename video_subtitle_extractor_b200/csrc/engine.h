@@ -121,6 +121,9 @@ struct LoadedPlan {
     std::vector<TcWeights> tcw_pk;   // pixel-packed block-diagonal variants (n_chunk == 0 => none)
     std::vector<size_t> tcw_pk_off;
     DevBuf tc_weights;
+    // 2x2 stride-2 transposed convolutions on the tensor-core path: one weight matrix [cout][cin] per output position
+    std::vector<TcWeights> tcw_dc;   // [step * 4 + pos] (n_chunk == 0 => not packed)
+    std::vector<size_t> tcw_dc_off;
     std::vector<float> a_scale;      // per step: power of two applied to a convolution's operand rows in split mode
     bool loaded = false;
 };
@@ -142,6 +145,7 @@ struct ExecContext {
         int64_t pix_off = 0;   // first pixel of the group in the step's input / output / residual values
     };
     std::vector<std::vector<TcGroup>> tc_groups;
+    std::vector<TcConv> tc_dc;      // [step * 4 + pos]: the four 1x1 launches of a transposed convolution (valid => tensor cores)
     DevBuf tc_gdev;                 // per ragged step: the groups' tensor maps + geometry table on the device (gemm_tc.h)
     std::vector<size_t> tc_goff;    // byte offset of a step's table in tc_gdev
     std::vector<char> tc_gup;       // 1 = the table on the device is current

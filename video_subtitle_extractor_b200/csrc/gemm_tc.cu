@@ -1069,7 +1069,8 @@ static std::string tc_output_map(TcConv& t, bool* changed = nullptr) {
     const cuuint32_t cols = cuuint32_t(128 / es);   // one staging row = 64 fp16 or 32 fp32 columns
     if (t.spatial) {
         cuuint64_t dims[4] = {cuuint64_t(t.n_store), cuuint64_t(t.W), cuuint64_t(t.H), cuuint64_t(t.n_img)};
-        cuuint64_t strides[3] = {cuuint64_t(t.out_cs) * es, cuuint64_t(t.W) * t.out_cs * es, cuuint64_t(t.H) * t.W * t.out_cs * es};
+        cuuint64_t strides[3] = {cuuint64_t(t.o_px ? t.o_px : t.out_cs) * es, cuuint64_t(t.o_row ? t.o_row : (long long)t.W * t.out_cs) * es,
+                                 cuuint64_t(t.o_img ? t.o_img : (long long)t.H * t.W * t.out_cs) * es};
         cuuint32_t box[4] = {cols, cuuint32_t(t.halo ? 8 : 16), cuuint32_t(t.halo ? 16 : 8), 1};
         err = encode(&t.map_o, t.out, 4, dims, strides, box, es == 4);
     } else {

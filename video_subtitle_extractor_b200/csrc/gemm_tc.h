@@ -60,6 +60,10 @@ struct TcConv {
     int num_m_tiles = 0;
     void* out = nullptr;
     int out_cs = 0;
+    // spatial launches: element strides of the OUTPUT tensor between consecutive pixels / rows / images (0 = dense:
+    // out_cs, W * out_cs, H * W * out_cs).  A 2x2 stride-2 transposed convolution is four 1x1 convolutions whose outputs
+    // interleave: position (dy, dx) writes every other pixel of every other row (engine.cu, OP_DECONV2)
+    long long o_px = 0, o_row = 0, o_img = 0;
     Epilogue epi;
     bool valid = false;
 };

@@ -164,6 +164,7 @@ class Engine:
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
         self._check(self.lib.vse_load_plan(self._h, which, C.cast(buf, C.c_void_p), len(blob)), "vse_load_plan")
         self.plan_names[which] = name
+        self._last_blob = blob
         if name:
             self._apply_calibration(which, name)
 
@@ -176,6 +177,13 @@ class Engine:
             return
         with open(path) as f:
             cal = json.load(f)
+        from . import plan as _P
+        n_steps = _P.blob_step_count(self._last_blob)
+        if int(cal["n_steps"]) != n_steps:
+            import warnings
+            warnings.warn(f"vse_b200: calibration file {os.path.basename(path)} was made for a plan with {cal['n_steps']} steps, this "
+                          f"plan has {n_steps}: re-run tools/calibrate_ranges.py (default operand scales are used)", RuntimeWarning)
+            return
         arr = np.zeros(int(cal["n_steps"]), np.float32)
         for k, v in cal["conv_input_absmax"].items():
             arr[int(k)] = v

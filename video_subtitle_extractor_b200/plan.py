@@ -727,6 +727,39 @@ def _fuse(values: List[Value], nodes: List[Step], keep: set) -> List[Step]:
     return [s for idx, s in enumerate(nodes) if not dead[idx]]
 
 
+def _reorder_concats(values: List[Value], nodes: List[Step], keep: set) -> None:
+    """Concat buffers that are only read by dense convolutions may hold their slices in any order, as long as the
+    convolutions' input channels are permuted the same way.  Slices whose width is a multiple of CPAD go first, so that
+    their producers can write them in place (`_resolve_concat` needs CPAD-aligned offsets): PFHeadLocal of the server
+    detector concatenates a 1-channel map BEFORE a 64-channel one (V4/ch_det, ops #318-321) — in graph order the 64-channel
+    full-resolution slice starts at channel 1 and costs a copy of the largest activation of the whole network."""
+    copies: Dict[int, List[Step]] = {}
+    for s in nodes:
+        if s.op == OP_COPY:
+            copies.setdefault(s.out, []).append(s)
+    cons = _consumers(nodes)
+    for root, cps in copies.items():
+        if root in keep or len(cps) < 2:
+            continue
+        users = [nodes[i] for i in cons.get(root, []) if nodes[i].op != OP_COPY or nodes[i].out != root]
+        if not users or any(u.op != OP_CONV or u.ins[0] != root or root in u.ins[1:] for u in users):
+            continue
+        cps_sorted = sorted(cps, key=lambda c: c.p["coff"])
+        if all(c.p["coff"] % CPAD == 0 for c in cps_sorted):
+            continue
+        order = sorted(cps_sorted, key=lambda c: 0 if c.p["c"] % CPAD == 0 else 1)       # stable
+        perm: List[int] = []                                                             # new channel -> old channel
+        off = 0
+        for c in order:
+            perm += list(range(c.p["coff"], c.p["coff"] + c.p["c"]))
+            c.p["coff"] = off
+            off += c.p["c"]
+        if sorted(perm) != list(range(values[root].channels)):
+            raise PlanError("concat slices do not tile the buffer")
+        for u in users:
+            u.w["weight"] = np.ascontiguousarray(u.w["weight"][..., perm])                # [cout][kh][kw][cin]
+
+
 def _resolve_concat(values: List[Value], nodes: List[Step], input_vid: int) -> List[Step]:
     """Turn COPY-into-concat into aliasing when the producer can write the slice directly."""
     producers: Dict[int, int] = {}
@@ -874,6 +907,7 @@ def compile_model(model: Model, name: str = "", norm_scale=(1.0, 1.0, 1.0), norm
             needed.update(nodes[idx].ins)
     nodes = [n for n, k in zip(nodes, keep_nodes) if k]
     nodes = _fuse(low.values, nodes, keep=set(out_vids))
+    _reorder_concats(low.values, nodes, set(out_vids))
     nodes = _resolve_concat(low.values, nodes, low.input_vid)
     # fetched values leave the engine as dense float32 [pixels][channels]
     cons = _consumers(nodes)
@@ -902,6 +936,15 @@ def compile_model(model: Model, name: str = "", norm_scale=(1.0, 1.0, 1.0), norm
 DET_NORM = (tuple(1.0 / (255.0 * s) for s in (0.229, 0.224, 0.225)),
             tuple(-m / s for m, s in zip((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))))
 REC_NORM = ((1.0 / 127.5,) * 3, (-1.0,) * 3)
+
+
+def blob_step_count(blob: bytes) -> int:
+    """Number of steps of a packed plan (header field n_steps, csrc/plan.h::PlanHeader)."""
+    import struct
+    magic, version, n_values, n_steps = struct.unpack_from("<4I", blob, 0)
+    if magic != PLAN_MAGIC:
+        raise ValueError("not a packed plan")
+    return int(n_steps)
 
 
 def deserialize(blob: bytes) -> Plan:
