@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--det", default=None, help="detector model (default V4/ch_det_fast = BASELINE configs[1]); needs its packed plan")
     ap.add_argument("--rec", default=None, help="recogniser model (default V4/en_rec_fast)")
     ap.add_argument("--flags", type=int, default=0, help="vse_config.flags (VSE_FLAG_* A/B switches, profiling only)")
-    ap.add_argument("--precision", default=None, choices=["fp16", "fp32", "tf32", "fp32_tc"],
+    ap.add_argument("--precision", default=None, choices=["fp16", "fp32", "tf32", "fp32_tc", "mixed"],
                     help="activation / product precision (default: engine.bench_mode(), the mode held to the parity bar)")
     ap.add_argument("--frame-stride", type=int, default=7, help="synthetic stream index step between consecutive frames of the pool")
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
@@ -87,10 +87,16 @@ def apply_model_args(args):
         REC = args.rec
 
 
-def frame_index(p: int, k: int, world_b: int, stride: int) -> int:
-    """Index into the synthetic stream of frame k of global batch p: consecutive frames are `stride` stream frames apart, so a
-    pool of 3 x 32 frames walks over ~11 subtitles (45 frames of text + 15 blank each), not 2."""
-    return (p * world_b + k) * stride
+def frame_index(p: int, k: int, world_b: int, stride: int, per_rank: int = 0) -> int:
+    """Index into the synthetic stream of frame k of global batch p.  Consecutive frames of a rank are `stride` stream frames
+    apart, so a pool of 3 x 32 frames walks over ~11 subtitles (45 frames of text + 15 blank each), not 2.  Weak scaling wants
+    the SAME work on every GPU at every N: rank r (= k // per_rank) gets the N = 1 frame set shifted by r stream frames — the same
+    subtitles, other frames (noise, background phase).  Cutting ONE stream into contiguous ranges (what shard.frame_range does for
+    a real job) hands the ranks different text densities (26-41 lines per step at N = 8, profiles/r02_bench_n8.json) and the
+    max-over-ranks time then measures the stream's imbalance, not the system."""
+    per_rank = per_rank or world_b
+    r, slot = divmod(k, per_rank)
+    return (p * per_rank + slot) * stride + r
 
 
 def workload_config(args, world: int):
@@ -100,7 +106,8 @@ def workload_config(args, world: int):
     return {"workload": f"{src}, {DET} + {REC}", "baseline_config": args.config,
             "frames_per_step_per_gpu": B, "global_frames_per_step": world * B, "frame": [H, W, 3],
             "parallelism": f"frame-range sharding x{world}",
-            "frames": f"stream index (pool_batch * {world * B} + k) * {args.frame_stride}, {args.pool} pool batches cycled",
+            "frames": f"rank r, slot k of pool batch p: stream index (p * {B} + k) * {args.frame_stride} + r (every rank gets the N = 1 frame "
+                      f"set shifted by r stream frames), {args.pool} pool batches cycled",
             "l2": f"inputs larger than L2: {args.pool} distinct batches x {B * H * W * 3 / 1e6:.0f} MB cycled"}
 
 
@@ -206,11 +213,11 @@ def run_reference(args, rank, world):
     B = args.batch
     pick = [k * (B // per_step) for k in range(per_step)]
     if args.video:
-        vf = video_frames_at(args.video, [frame_index(p, k, world * B, args.frame_stride) for p in range(args.pool) for k in pick])
-        frames = {(p, k): vf[frame_index(p, k, world * B, args.frame_stride)] for p in range(args.pool) for k in pick}
+        vf = video_frames_at(args.video, [frame_index(p, k, world * B, args.frame_stride, B) for p in range(args.pool) for k in pick])
+        frames = {(p, k): vf[frame_index(p, k, world * B, args.frame_stride, B)] for p in range(args.pool) for k in pick}
         args.height, args.width = next(iter(vf.values())).shape[:2]
     else:
-        frames = {(p, k): stream.frame(frame_index(p, k, world * B, args.frame_stride)) for p in range(args.pool) for k in pick}
+        frames = {(p, k): stream.frame(frame_index(p, k, world * B, args.frame_stride, B)) for p in range(args.pool) for k in pick}
     for _ in range(max(args.warmup, 1)):
         oracle.ocr(frames[(0, 0)])
     t0 = time.perf_counter()
@@ -351,7 +358,7 @@ def run_b200(args, rank, local_rank, world):
     stream = SynthStream(H, W)
     video_frames = {}
     if args.video:      # real frames: every frame_stride-th frame of the video, decoded once up front
-        video_frames = video_frames_at(args.video, [frame_index(p, k, world * B, args.frame_stride) for p in range(args.pool)
+        video_frames = video_frames_at(args.video, [frame_index(p, k, world * B, args.frame_stride, B) for p in range(args.pool)
                                                     for k in range(world * B)])
         H, W = next(iter(video_frames.values())).shape[:2]
         args.height, args.width = H, W
@@ -359,7 +366,7 @@ def run_b200(args, rank, local_rank, world):
     host_batches, dev_batches = [], []
     for p in range(args.pool):
         lo, hi = shard.frame_range(rank, world, world * B)
-        idx = [frame_index(p, k, world * B, args.frame_stride) for k in range(lo, hi)]
+        idx = [frame_index(p, k, world * B, args.frame_stride, B) for k in range(lo, hi)]
         pinned = torch.empty((len(idx), H, W, 3), dtype=torch.uint8, pin_memory=True)
         arr = pinned.numpy()
         for j, i in enumerate(idx):
@@ -371,15 +378,21 @@ def run_b200(args, rank, local_rank, world):
     # V2 recognisers (ResNet + BiLSTM) read 32-pixel-high crops (reference backend/tools/paddle_model_config.py:94-97)
     rec_h = 32 if REC.startswith("V2/") else 48
     mode = dict(E.bench_mode())
-    if args.precision:
-        mode["precision"] = {"fp16": E.PRECISION_FP16, "fp32": E.PRECISION_FP32, "tf32": E.PRECISION_TF32,
-                             "fp32_tc": E.PRECISION_FP32_TC}[args.precision]
+    if args.precision == "mixed":
+        mode = dict(E.mixed_mode())
+    elif args.precision:
+        mode = dict(precision={"fp16": E.PRECISION_FP16, "fp32": E.PRECISION_FP32, "tf32": E.PRECISION_TF32,
+                               "fp32_tc": E.PRECISION_FP32_TC}[args.precision])
     mode["flags"] = mode.get("flags", 0) | args.flags
+    det_split = bool(mode["flags"] & E.FLAG_DET_FP32_TC) and mode["precision"] == E.PRECISION_FP16
     prec_name = {E.PRECISION_FP16: "fp16 activations, fp32 accumulate (NOT the parity mode: DESIGN.md §5)",
                  E.PRECISION_FP32: "fp32 activations, CUDA-core kernels",
                  E.PRECISION_TF32: "fp32 activations, tf32 tensor-core products",
                  E.PRECISION_FP32_TC: "fp32 activations; tensor-core products on fp16 hi+lo splits of both operands "
                                       "(3 MMAs per product), fp32 accumulate"}[mode["precision"]]
+    if det_split:
+        prec_name = ("detector: fp32 activations, tensor-core products on fp16 hi+lo splits of both operands (3 MMAs per product); "
+                     "recogniser: fp16 activations, fp32 accumulate")
     eng = E.Engine(device=local_rank, rec_image_h=rec_h, **mode)
     eng.load_plan(E.PLAN_DET, det_blob, DET)
     eng.load_plan(E.PLAN_REC, rec_blob, REC)
@@ -481,7 +494,9 @@ def run_b200(args, rank, local_rank, world):
                 pass
             roofline.update({"bound": "tensor", "achieved": roofline["tflops"], "peak": tpeak, "unit": "TFLOP/s",
                              "frac": roofline["tflops"] / tpeak, "peak_source": tsrc, "hbm_gbs": achieved,
-                             "note": "algorithmic FLOPs; the mode issues 3 fp16 MMAs per product (hi*Wh + lo*Wh + hi*Wl)"})
+                             "executed_tflops": 3 * roofline["tflops"], "executed_frac": 3 * roofline["tflops"] / tpeak,
+                             "note": "achieved / frac count ALGORITHMIC FLOPs (one product per multiply-add); the fp32 tensor-core mode "
+                                     "issues 3 fp16 MMAs per product (hi*Wh + lo*Wh + hi*Wl): executed_* is the rate the tensor pipe runs at"})
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             oracle, cores = cpu_oracle(det_blob, rec_blob)
@@ -495,7 +510,7 @@ def run_b200(args, rank, local_rank, world):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16" if mode["precision"] == E.PRECISION_FP16 else "f32", "data": "real video frames" if args.video else "synthetic",
+            "dtype": "f32+f16" if det_split else "f16" if mode["precision"] == E.PRECISION_FP16 else "f32", "data": "real video frames" if args.video else "synthetic",
             "config": workload_config(args, world),
             "precision": prec_name + (f"; vse_config.flags={args.flags}" if args.flags else ""),
             "text_lines_per_frame": n_lines / max(args.steps * B, 1), "mean_padded_rec_width": mean_width,

@@ -63,7 +63,11 @@ enum {
     /* not an A/B switch: run the DETECTOR plan with fp32 activations whatever vse_config.precision says (V4/ch_det, the
      * accurate-mode detector of backend/tools/paddle_model_config.py:60,70, exceeds the fp16 range) */
     VSE_FLAG_DET_FP32 = 1024,
-    VSE_FLAG_DET_TF32 = 2048   /* same, with the detector's convolutions on the tf32 tensor-core path */
+    VSE_FLAG_DET_TF32 = 2048,  /* same, with the detector's convolutions on the tf32 tensor-core path */
+    /* the DETECTOR plan in VSE_PRECISION_FP32_TC whatever vse_config.precision says: with precision = VSE_PRECISION_FP16 the
+     * recogniser keeps fp16 activations (its bar is CER <= 1e-3 on class ids, which fp16 meets on the reference's videos) while
+     * the detector — whose 0.3 threshold crossing needs ~1e-5 on the probability map — keeps fp32 activations */
+    VSE_FLAG_DET_FP32_TC = 8192
 };
 
 /* Mirrors the knobs the reference passes to PaddleOCR / TextDetector (ocr.py:91-113) and the

@@ -105,9 +105,13 @@ def run_schedule(golden, eng, batch=32):
 
 
 CASES = [("test_en", "V4/ch_det_fast", "V4/en_rec_fast"), ("test_cn", "V4/ch_det_fast", "V4/ch_rec_fast")]
-MODES = [("bench", None), ("fp32", E.PRECISION_FP32), ("fp32_tc", E.PRECISION_FP32_TC), ("fp16", E.PRECISION_FP16)]
-# modes that are measured and recorded but not held to the bar (fp16 storage moves the 0.3 threshold crossing: DESIGN.md §5)
-REPORT_ONLY = {"fp16"}
+MODES = [("bench", None), ("fp32", E.PRECISION_FP32), ("fp32_tc", E.PRECISION_FP32_TC), ("fp16", E.PRECISION_FP16),
+         # detector in the fp32 tensor-core mode (boxes), recogniser with fp16 activations (class ids)
+         ("mixed", dict(precision=E.PRECISION_FP16, flags=E.FLAG_DET_FP32_TC))]
+# modes that are measured and recorded but not held to the bar: fp16 storage moves the 0.3 threshold crossing of the detector
+# (DESIGN.md §5); "mixed" keeps every box and every en line but flips ~3 % of the 6625-class Chinese lines (CER 4.6e-3 on
+# test_cn, profiles/r02_real_video_parity.json) — fp16 logits cannot separate near-tied classes of the big dictionary
+REPORT_ONLY = {"fp16", "mixed"}
 
 
 @pytest.mark.parametrize("mode,prec", MODES)
@@ -121,7 +125,7 @@ def test_whole_fast_mode_schedule_matches_graph_oracle(video, det, rec, mode, pr
         pytest.skip("tests/golden/_videos/ is absent (run __graft_entry__.build() where the reference tree exists)")
     if not (weights.have_plan(det) and weights.have_plan(rec)):
         pytest.skip("packed plans not present on this machine")
-    kw = E.bench_mode() if prec is None else dict(precision=prec)
+    kw = E.bench_mode() if prec is None else prec if isinstance(prec, dict) else dict(precision=prec)
     eng = E.Engine(**kw)
     eng.load_plan(E.PLAN_DET, weights.load_plan_blob(det), det)
     eng.load_plan(E.PLAN_REC, weights.load_plan_blob(rec), rec)
@@ -133,7 +137,7 @@ def test_whole_fast_mode_schedule_matches_graph_oracle(video, det, rec, mode, pr
     if os.path.exists(rec_path):
         with open(rec_path) as f:
             allr = json.load(f)
-    allr[f"{video}:{mode}"] = dict(st, engine=kw if prec is None else {"precision": prec}, models=[det, rec])
+    allr[f"{video}:{mode}"] = dict(st, engine=kw, models=[det, rec])
     with open(rec_path, "w") as f:
         json.dump(allr, f, indent=1)
     print(f"\n{video} [{mode}]: {st['frames']} frames, {st['boxes']} boxes, count mismatch {st['count_mismatch']}, not identical "

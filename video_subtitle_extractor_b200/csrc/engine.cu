@@ -59,6 +59,7 @@ void Engine::load_plan(int which, const void* blob, size_t n) {
     plan_prec_[which] = cfg.precision;
     if (which == 0 && (cfg.flags & VSE_FLAG_DET_FP32)) plan_prec_[which] = VSE_PRECISION_FP32;
     if (which == 0 && (cfg.flags & VSE_FLAG_DET_TF32)) plan_prec_[which] = VSE_PRECISION_TF32;
+    if (which == 0 && (cfg.flags & VSE_FLAG_DET_FP32_TC)) plan_prec_[which] = VSE_PRECISION_FP32_TC;
     if (plan_prec_[which] < VSE_PRECISION_FP16 || plan_prec_[which] > VSE_PRECISION_FP32_TC) throw InvalidArg{"bad precision"};
     prepare_plan(which, lp);
     lp.loaded = true;

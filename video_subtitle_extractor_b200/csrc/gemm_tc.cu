@@ -42,7 +42,8 @@ static constexpr int kMaxSmem = 227 * 1024;
 
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
-        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems, split, kbb, out_bufs;
+        stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems, split, kbb, out_bufs,
+        tw_shift, tile_h;   // spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
     void* out;
     int out_cs;
     const float* bias;
@@ -441,9 +442,9 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
             const int per_img = tg.tiles_x * tg.tiles_y;
             img = tg.m_local / per_img;
             const int r = tg.m_local - img * per_img;
-            y0 = (r / tg.tiles_x) * (p.halo ? 16 : 8);
-            x0 = (r % tg.tiles_x) * (p.halo ? 8 : 16);
-            const int y = y0 + (p.halo ? row >> 3 : row >> 4), x = x0 + (p.halo ? row & 7 : row & 15);
+            y0 = (r / tg.tiles_x) * p.tile_h;
+            x0 = (r % tg.tiles_x) << p.tw_shift;
+            const int y = y0 + (row >> p.tw_shift), x = x0 + (row & ((1 << p.tw_shift) - 1));
             if (y < tg.H && x < tg.W) pix = tg.pix_off + (long long)img * tg.H * tg.W + (long long)y * tg.W + x;
         } else {
             const long long m = (long long)m_tile * BLOCK_M + row;
@@ -743,8 +744,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int per_img = tg.tiles_x * tg.tiles_y;
                     img = tg.m_local / per_img;
                     const int r = tg.m_local - img * per_img;
-                    y0 = (r / tg.tiles_x) * (p.halo ? 16 : 8);
-                    x0 = (r % tg.tiles_x) * (p.halo ? 8 : 16);
+                    y0 = (r / tg.tiles_x) * p.tile_h;
+                    x0 = (r % tg.tiles_x) << p.tw_shift;
                 }
                 for (int it = 0; it < k_iters; it++) {
                     const int tap = it / p.num_kb, kb = it - tap * p.num_kb;   // rowbox: tap = kx
@@ -1035,8 +1036,12 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         const int h_stage = round_up_i(h_box, 1024) + (t.b_resident ? 0 : kh * kw * w.n_chunk * 128);
         t.halo = (allow_halo && kh > 1 && kh <= 5 && kw <= 5 && kw > 1 &&
                   3 * h_stage + (t.b_resident ? b_all : 0) <= kMaxSmem - slack - (w.split ? 2 : kOutBufs) * kOutBufBytes) ? 1 : 0;
-        t.tiles_x = t.halo ? (W + 7) / 8 : (W + 15) / 16;
-        t.tiles_y = t.halo ? (H + 15) / 16 : (H + 7) / 8;
+        // tile shape: 8 x 16 (halo), 16 x 8, or — maps of height 1 (the recogniser's sequence part: 1 x kw convolutions over
+        // text lines) — one row of 128 columns: a 16 x 8 tile would spend 7/8 of its rows on nothing
+        t.tile_w = t.halo ? 8 : (H == 1 && kh == 1) ? 128 : 16;
+        t.tile_h = 128 / t.tile_w;
+        t.tiles_x = (W + t.tile_w - 1) / t.tile_w;
+        t.tiles_y = (H + t.tile_h - 1) / t.tile_h;
         t.num_m_tiles = n_img * t.tiles_x * t.tiles_y;
         cuuint64_t dims[4] = {cuuint64_t(cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(n_img)};
         cuuint64_t strides[3] = {cuuint64_t(in_cs) * es, cuuint64_t(W) * in_cs * es, cuuint64_t(H) * W * in_cs * es};
@@ -1044,8 +1049,8 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         // traffic for the activations.  Needs >= 3 pipeline stages of (box + kh weight slices) in shared memory.
         const int a_box = (8 + kh - 1) * 16 * 128;
         const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + kh * w.n_chunk * 128);
-        t.rowbox = (!t.halo && allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - slack - (w.split ? 2 : kOutBufs) * kOutBufBytes) ? 1 : 0;
-        cuuint32_t box[4] = {kbe, cuuint32_t(t.halo ? 8 + kw - 1 : 16), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + kh - 1 : 8), 1};
+        t.rowbox = (!t.halo && t.tile_w == 16 && allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - slack - (w.split ? 2 : kOutBufs) * kOutBufBytes) ? 1 : 0;
+        cuuint32_t box[4] = {kbe, cuuint32_t(t.halo ? 8 + kw - 1 : t.tile_w), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + kh - 1 : t.tile_h), 1};
         err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box, a32);
     }
     if (!err.empty()) return err;
@@ -1071,7 +1076,7 @@ static std::string tc_output_map(TcConv& t, bool* changed = nullptr) {
         cuuint64_t dims[4] = {cuuint64_t(t.n_store), cuuint64_t(t.W), cuuint64_t(t.H), cuuint64_t(t.n_img)};
         cuuint64_t strides[3] = {cuuint64_t(t.o_px ? t.o_px : t.out_cs) * es, cuuint64_t(t.o_row ? t.o_row : (long long)t.W * t.out_cs) * es,
                                  cuuint64_t(t.o_img ? t.o_img : (long long)t.H * t.W * t.out_cs) * es};
-        cuuint32_t box[4] = {cols, cuuint32_t(t.halo ? 8 : 16), cuuint32_t(t.halo ? 16 : 8), 1};
+        cuuint32_t box[4] = {cols, cuuint32_t(t.tile_w), cuuint32_t(t.tile_h), 1};
         err = encode(&t.map_o, t.out, 4, dims, strides, box, es == 4);
     } else {
         cuuint64_t dims[2] = {cuuint64_t(t.n_store), cuuint64_t(t.M)};
@@ -1108,7 +1113,7 @@ std::string launch_conv_tc_groups(TcConv* const* gs, const long long* pix_off, i
     bool changed = !*uploaded;
     for (int g = 0; g < n_groups; g++) {
         TcConv& t = *gs[g];
-        if (!t.spatial || t.halo != gs[0]->halo || t.rowbox != gs[0]->rowbox || t.b_resident != gs[0]->b_resident || t.num_kb != gs[0]->num_kb)
+        if (!t.spatial || t.halo != gs[0]->halo || t.rowbox != gs[0]->rowbox || t.tile_w != gs[0]->tile_w || t.b_resident != gs[0]->b_resident || t.num_kb != gs[0]->num_kb)
             return "groups with different kernel shapes";
         if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (of32 ? 3 : 7))) return "output view not 16-byte aligned";
         std::string err = tc_output_map(t, &changed);
@@ -1152,6 +1157,8 @@ static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const C
     p.kbb = t.split ? 64 : p.kb_elems;             // weight columns per k-block
     p.rowbox = t.rowbox;
     p.halo = t.halo;
+    p.tile_h = t.tile_h;
+    p.tw_shift = t.tile_w == 8 ? 3 : t.tile_w == 16 ? 4 : 7;
     p.a_tx = t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh - 1) * 16 * 128 : A_BYTES;
     p.a_bytes = round_up_i(p.a_tx, 1024);
     p.n_total = t.n_chunk * t.n_chunks;

@@ -44,6 +44,7 @@ struct TcConv {
     int spatial = 0;        // 0: 1x1 over a flat pixel list; 1: KxK stride 1 over equal-sized images
     int M = 0;              // flat: number of pixels
     int n_img = 0, H = 0, W = 0, tiles_x = 0, tiles_y = 0;
+    int tile_w = 16, tile_h = 8;   // spatial tile (128 pixels): 8 x 16 halo, 16 x 8, 128 x 1 for maps of height 1
     int kh = 1, kw = 1, ph = 0, pw = 0;
     int cin = 0;            // real input channels (the MMA loop skips the all-zero tail of the last K block)
     int rowbox = 0;         // KxK: A boxes span 8 + kh - 1 image rows and serve all vertical taps (see gemm_tc.cu)

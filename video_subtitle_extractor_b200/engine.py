@@ -24,6 +24,7 @@ FLAG_NO_FUSED_HEAD, FLAG_NO_SE_FUSION, FLAG_NO_ROWBOX, FLAG_NO_FAST_DW, FLAG_NO_
 FLAG_NO_CONCAT_GATHER, FLAG_NO_HALO = 256, 512
 FLAG_DET_FP32, FLAG_DET_TF32 = 1024, 2048
 FLAG_NO_SE_CONV = 4096
+FLAG_DET_FP32_TC = 8192
 
 
 class VseConfig(C.Structure):
@@ -93,6 +94,13 @@ def bench_mode() -> dict:
     activation storage is ~1.5x faster but moves the 0.3 threshold crossing of the detector on ~1 % of real-video boxes
     (tests/test_gpu_real_video.py reports it), so it is not the mode that is timed."""
     return dict(precision=PRECISION_FP32_TC)
+
+
+def mixed_mode() -> dict:
+    """Detector in the fp32 tensor-core mode (its boxes hang on the 0.3 threshold crossing of the probability map), recogniser
+    with fp16 activations (its bar is CER <= 1e-3 on the class ids; tests/test_gpu_real_video.py measures it on the reference's
+    sample videos as mode "mixed")."""
+    return dict(precision=PRECISION_FP16, flags=FLAG_DET_FP32_TC)
 
 
 def accurate_mode() -> dict:
