@@ -43,7 +43,7 @@ static constexpr int kMaxSmem = 227 * 1024;
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
         stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems, split, kbb, out_bufs,
-        tw_shift, tile_h;   // spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
+        stack, acc_cols, tw_shift, tile_h;   // stack: see 'stacked split' (umma_kblock); acc_cols: TMEM columns per accumulator; spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
     void* out;
     int out_cs;
     const float* bias;
@@ -202,6 +202,21 @@ __device__ __forceinline__ void umma_f16_words2(uint32_t d_tmem, uint32_t a_lo, 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(a_hi)
+        : "memory");
+}
+// both descriptors' high words given (the stacked split reads its weights through a SWIZZLE_64B descriptor)
+__device__ __forceinline__ void umma_f16_words3(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 da, {%1, %6};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(b_hi), "r"(a_hi)
         : "memory");
 }
 // kind::tf32: fp32 operands in shared memory (rounded to tf32 by the tensor core), 8 elements (32 bytes) of K per instruction
@@ -453,7 +468,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
         const float* grow = (GATE && p.gate && pix >= 0) ? p.gate + size_t(pix / p.gate_rows) * p.gate_c : nullptr;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.n_chunk);
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.acc_cols);
         const int ch0 = n_idx * p.n_chunk;
         for (int sub = 0; sub < n_sub; sub++) {
             if (ch0 + sub * SUBC >= p.n_store) break;                  // uniform over the 8 warps
@@ -464,7 +479,15 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                 if constexpr (OUTF32) {
                     uint32_t raw0[16];
                     tmem_ld16_nowait(taddr + uint32_t(c0), raw0);       // .sync.aligned: whole (converged) warp
-                    tmem_ld_wait();
+                    if (p.stack) {                                      // stacked split: hi * Wl lives n_chunk columns further
+                        uint32_t rawl[16];
+                        tmem_ld16_nowait(taddr + uint32_t(p.n_chunk + c0), rawl);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) raw0[j] = __float_as_uint(__uint_as_float(raw0[j]) + __uint_as_float(rawl[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     uint4 o[4];
                     epi_chunk16<ACT, POST, true, PSM, GATE>(e, raw0, ch0 + c0, pix, o, grow);
 #pragma unroll
@@ -564,15 +587,28 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const CUten
 // one k-block of one filter tap: up to four K = 32-byte MMAs — or, in split mode, the six MMAs of the 3-term product: the
 // operand row is [hi(32 ch) | lo(32 ch)] (fp16, written in place by the transform warps), the weight row [Wh(32) | Wl(32)]:
 //   hi * Wh (2 MMAs), lo * Wh (2), hi * Wl (2); lo * Wl (2^-22 relative) is dropped.
+// Stacked split (narrow, K-heavy layers: N <= 32, where an MMA's time is the fetch of its 128 A rows, not the math): the weight
+// slice of a k-block is [2n rows x 64 B] (SWIZZLE_64B) — rows [0, n) hold Wh, rows [n, 2n) Wl — so ONE N = 2n MMA on the hi rows
+// yields hi * Wh (columns [0, n)) and hi * Wl (columns [n, 2n)), and one N = n MMA on the lo rows adds lo * Wh to the first n
+// columns: four MMAs / two A fetches per 16 channels x 2 instead of six / three.  The epilogue adds the two column groups.
+static constexpr uint32_t kDescHi64 = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B (8 rows of 64 B), version 1, SWIZZLE_64B
 template <bool TF32, bool SPLIT>
-__device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a, uint32_t a_hi, uint32_t b, uint32_t idesc, uint32_t acc_first, int ks) {
+__device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a, uint32_t a_hi, uint32_t b, uint32_t idesc, uint32_t acc_first, int ks,
+                                            uint32_t idesc2 = 0) {
     if constexpr (SPLIT) {
-        umma_f16_words2(d_tmem, a, a_hi, b, idesc, acc_first);
-        umma_f16_words2(d_tmem, a + 2, a_hi, b + 2, idesc, 1u);
-        umma_f16_words2(d_tmem, a + 4, a_hi, b, idesc, 1u);
-        umma_f16_words2(d_tmem, a + 6, a_hi, b + 2, idesc, 1u);
-        umma_f16_words2(d_tmem, a, a_hi, b + 4, idesc, 1u);
-        umma_f16_words2(d_tmem, a + 2, a_hi, b + 6, idesc, 1u);
+        if (idesc2 != 0) {
+            umma_f16_words3(d_tmem, a, a_hi, b, kDescHi64, idesc2, acc_first);
+            umma_f16_words3(d_tmem, a + 2, a_hi, b + 2, kDescHi64, idesc2, 1u);
+            umma_f16_words3(d_tmem, a + 4, a_hi, b, kDescHi64, idesc, 1u);
+            umma_f16_words3(d_tmem, a + 6, a_hi, b + 2, kDescHi64, idesc, 1u);
+        } else {
+            umma_f16_words2(d_tmem, a, a_hi, b, idesc, acc_first);
+            umma_f16_words2(d_tmem, a + 2, a_hi, b + 2, idesc, 1u);
+            umma_f16_words2(d_tmem, a + 4, a_hi, b, idesc, 1u);
+            umma_f16_words2(d_tmem, a + 6, a_hi, b + 2, idesc, 1u);
+            umma_f16_words2(d_tmem, a, a_hi, b + 4, idesc, 1u);
+            umma_f16_words2(d_tmem, a + 2, a_hi, b + 6, idesc, 1u);
+        }
     } else {
         umma_words<TF32>(d_tmem, a, a_hi, b, idesc, acc_first);
         if (ks > 1) umma_words<TF32>(d_tmem, a + 2, a_hi, b + 2, idesc, 1u);
@@ -588,6 +624,7 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
     const int KH = KH_ ? KH_ : p.kh, KW = KW_ ? KW_ : p.kw;
     // instruction descriptor: D = f32, A/B = f16 (kind::f16) or tf32 (kind::tf32, format code 2), N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | (TF32 ? (2u << 7) | (2u << 10) : 0u) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+    const uint32_t idesc2 = (SPLIT && p.stack) ? ((1u << 4) | (uint32_t((2 * p.n_chunk) >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24)) : 0u;
     const int total_tiles = p.num_m_tiles * p.n_chunks;
     const int stages = p.stages, acc_stages = p.acc_stages, num_kb = p.num_kb, n_chunk = p.n_chunk;
     const bool resident = p.b_resident != 0;
@@ -608,7 +645,7 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * n_chunk);
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * p.acc_cols);
         int kb = 0;
         uint32_t b_it = bres_lo;                                     // resident slice of (k-iteration `it`)
         for (int it = 0; it < k_iters; it++) {
@@ -618,13 +655,13 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
             const uint32_t b_first = resident ? b_it : a_lo + a16;
             if (elect_one()) {
                 if constexpr (MODE == 0) {
-                    umma_kblock<TF32, SPLIT>(d_tmem, a_lo, kDescHi, b_first, idesc, it != 0 ? 1u : 0u, ks);
+                    umma_kblock<TF32, SPLIT>(d_tmem, a_lo, kDescHi, b_first, idesc, it != 0 ? 1u : 0u, ks, idesc2);
                 } else if constexpr (MODE == 1) {
 #pragma unroll
                     for (int ky = 0; ky < KH; ky++) {
                         const uint32_t a_t = a_lo + uint32_t(ky * 128);           // next image row of the box: 16 px * 128 B
                         const uint32_t b_t = b_first + uint32_t(ky) * b_ky_step;
-                        umma_kblock<TF32, SPLIT>(d_tmem, a_t, kDescHi, b_t, idesc, (it | ky) != 0 ? 1u : 0u, ks);
+                        umma_kblock<TF32, SPLIT>(d_tmem, a_t, kDescHi, b_t, idesc, (it | ky) != 0 ? 1u : 0u, ks, idesc2);
                     }
                 } else {
 #pragma unroll
@@ -633,7 +670,7 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
                         for (int kx = 0; kx < KW; kx++) {
                             const uint32_t a_t = a_lo + (uint32_t(ky) * bw + uint32_t(kx)) * 8u;   // pixel rows of 128 B
                             const uint32_t b_t = b_first + uint32_t(ky * KW + kx) * b_tap_step;
-                            umma_kblock<TF32, SPLIT>(d_tmem, a_t, halo_hi, b_t, idesc, (it | ky | kx) != 0 ? 1u : 0u, ks);
+                            umma_kblock<TF32, SPLIT>(d_tmem, a_t, halo_hi, b_t, idesc, (it | ky | kx) != 0 ? 1u : 0u, ks, idesc2);
                         }
                 }
                 umma_commit(&empty[stage]);                            // smem slot is free once these MMAs have read it
@@ -893,9 +930,11 @@ TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, int mode)
         t.n_chunks = (n_mma + 255) / 256;
         t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, t.n_chunks > 1 ? 64 : 16);
         const int num_kb = (cin + 31) / 32;
-        t.k_pad = num_kb * 64;                     // columns (halves) per tap
+        // narrow K-heavy layers (the 3x3 96 -> 24 convolutions of the FPN): hi / lo stacked along N, see umma_kblock
+        t.stack = (t.n_chunks == 1 && t.n_chunk <= 32 && taps * cin >= 256 && !getenv("VSE_NO_STACK")) ? 1 : 0;
+        t.k_pad = num_kb * (t.stack ? 32 : 64);    // columns (halves) per tap
         t.taps = taps;
-        const size_t rows = size_t(t.n_chunks) * t.n_chunk, cols = size_t(taps) * t.k_pad;
+        const size_t rows = size_t(t.n_chunks) * t.n_chunk * (t.stack ? 2 : 1), cols = size_t(taps) * t.k_pad;
         t.b.assign(rows * cols, 0);
         // power-of-two weight scale: max |w| * scale in [2^13, 2^14) keeps hi AND lo = w - hi of every weight that matters in
         // the fp16 normal range (the tensor core flushes subnormal inputs)
@@ -914,6 +953,12 @@ TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, int mode)
                     const float f = w[(size_t(co) * taps + tp) * cin + ci] * t.w_scale;
                     const __half h = __float2half_rn(f);
                     const __half l = __float2half_rn(f - __half2float(h));
+                    if (t.stack) {        // row co = hi, row n_chunk + co = lo; 32 columns per k-block
+                        const size_t at = size_t(co) * cols + size_t(tp) * t.k_pad + ci;
+                        std::memcpy(&t.b[at], &h, 2);
+                        std::memcpy(&t.b[at + size_t(t.n_chunk) * cols], &l, 2);
+                        continue;
+                    }
                     const size_t at = size_t(co) * cols + size_t(tp) * t.k_pad + size_t(ci / 32) * 64 + (ci % 32);
                     std::memcpy(&t.b[at], &h, 2);
                     std::memcpy(&t.b[at + 32], &l, 2);
@@ -983,13 +1028,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 static std::string encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                          const cuuint32_t* box, bool f32 = false) {
+                          const cuuint32_t* box, bool f32 = false, bool swizzle64 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return "cuTensorMapEncodeTiled unavailable";
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapL2promotion pr = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;   // 64B / 256B / none measured equal on these layers
     CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), base, dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")";
     return "";
 }
@@ -1007,6 +1052,7 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
     t.halo = 0;
     t.tf32 = w.tf32;
     t.split = w.split;
+    t.stack = w.split ? w.stack : 0;
     t.w_scale = w.split ? w.w_scale : 1.f;
     const int es = a32 ? 4 : 2;                  // activation element size
     const int es_b = w.tf32 ? 4 : 2;             // weight element size (split: fp16 hi | lo)
@@ -1055,10 +1101,11 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
     }
     if (!err.empty()) return err;
     {
-        cuuint64_t dims[2] = {cuuint64_t(w.taps) * w.k_pad, cuuint64_t(w.n_chunks) * w.n_chunk};
+        // stacked split: [2 n_chunk rows (hi | lo)] x [32 columns = 64 bytes per k-block], SWIZZLE_64B
+        cuuint64_t dims[2] = {cuuint64_t(w.taps) * w.k_pad, cuuint64_t(w.n_chunks) * w.n_chunk * (t.stack ? 2 : 1)};
         cuuint64_t strides[1] = {cuuint64_t(w.taps) * w.k_pad * es_b};
-        cuuint32_t box[2] = {cuuint32_t(128 / es_b), cuuint32_t(w.n_chunk)};
-        err = encode(&t.map_b, const_cast<void*>(wdev), 2, dims, strides, box, w.tf32);
+        cuuint32_t box[2] = {cuuint32_t((t.stack ? 64 : 128) / es_b), cuuint32_t(w.n_chunk * (t.stack ? 2 : 1))};
+        err = encode(&t.map_b, const_cast<void*>(wdev), 2, dims, strides, box, w.tf32, t.stack != 0);
         if (!err.empty()) return err;
     }
     t.valid = true;
@@ -1154,7 +1201,9 @@ static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const C
     p.tf32 = t.tf32;
     p.split = t.split;
     p.kb_elems = of32 ? 32 : BLOCK_K;              // activation elements per k-block
-    p.kbb = t.split ? 64 : p.kb_elems;             // weight columns per k-block
+    p.kbb = t.split ? (t.stack ? 32 : 64) : p.kb_elems;   // weight columns per k-block
+    p.stack = t.stack;
+    p.acc_cols = t.n_chunk * (t.stack ? 2 : 1);
     p.rowbox = t.rowbox;
     p.halo = t.halo;
     p.tile_h = t.tile_h;
@@ -1178,9 +1227,9 @@ static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const C
     p.stages = std::max(2, std::min(8, budget / stage_bytes));
     // TMEM accumulator ring: the MMA warp runs up to acc_stages tiles ahead of the epilogue (hides the commit -> wait ->
     // tcgen05.ld -> arrive round trip, which dominates layers with one k-iteration per tile)
-    p.acc_stages = std::max(2, std::min(kMaxAccStages, 512 / t.n_chunk));
+    p.acc_stages = std::max(2, std::min(kMaxAccStages, 512 / p.acc_cols));
     int cols = 32;
-    while (cols < p.acc_stages * t.n_chunk) cols *= 2;
+    while (cols < p.acc_stages * p.acc_cols) cols *= 2;
     p.tmem_cols = cols;
     p.out = t.out; p.out_cs = t.out_cs;
     p.bias = t.epi.bias; p.post_scale = t.epi.post_scale; p.post_shift = t.epi.post_shift;

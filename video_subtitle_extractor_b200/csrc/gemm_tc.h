@@ -20,6 +20,8 @@ struct TcWeights {          // built once per plan step (host), uploaded as fp16
     int tf32 = 0;           // 1: fp32 elements (tcgen05 kind::tf32), k_pad a multiple of 32; 0: fp16, multiple of 64
     int split = 0;          // 1: fp16 hi | lo halves of fp32 weights, 64 columns per 32 input channels (see gemm_tc.cu, "split" mode)
     float w_scale = 1.f;    // split: power of two the weights were multiplied by before the split
+    int stack = 0;          // split, narrow K-heavy layers: hi and lo weights stacked along N (rows [0, n) = hi, [n, 2n) = lo), 32 columns
+                            // (64 bytes, SWIZZLE_64B) per 32 input channels — see gemm_tc.cu, "stacked split"
     std::vector<uint16_t> b;  // raw 16-bit words: fp16 bits (or 2 words per fp32), [n_chunks * n_chunk][taps * k_pad], K-major, zero padded
 };
 
@@ -51,6 +53,7 @@ struct TcConv {
     int tf32 = 0;           // fp32 activations / weights through kind::tf32 MMAs, fp32 output
     int split = 0;          // fp32 activations split in place into fp16 hi | lo, three kind::f16 MMAs per product, fp32 output
     float w_scale = 1.f;
+    int stack = 0;          // split with hi / lo weights stacked along N (TcWeights::stack)
     float a_scale = 0.f;    // split: power of two for the operand rows (0 = the default of tc_split_activation_scale())
     int pack = 0;           // >0: pixel-packed flat conv (rows of `pack` pixels)
     int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
