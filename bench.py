@@ -561,7 +561,9 @@ def run_videos(args, rank, local_rank, world):
     def one_pass(stats):
         n_frames, n_lines, n_subs = 0, 0, 0
         for path, lang, rec, n_cls in jobs:
+            t_lp = time.perf_counter()
             eng.load_plan(E.PLAN_REC, weights.load_plan_blob(rec), rec)
+            stats["load_plan_s"] = stats.get("load_plan_s", 0.0) + time.perf_counter() - t_lp
             res = job.fast_mode_job(eng, path, charset.characters(lang, None, n_cls), rank=rank, world=world, batch=args.batch,
                                     rec_char_type=lang, stats=stats, write_srt=rank == 0)
             n_frames += res.frames_ocr
@@ -585,7 +587,8 @@ def run_videos(args, rank, local_rank, world):
     wall = time.perf_counter() - t0
     wall_max = shard.max_over_ranks(wall, dev)
     mine = (rank, n_frames, wall / args.steps, stats.get("feed_wait_s", 0) / args.steps, stats.get("engine_s", 0) / args.steps,
-            stats.get("frames_decoded", 0) // args.steps)
+            stats.get("frames_decoded", 0) // args.steps,
+            {k: round(stats.get(k, 0.0) / args.steps, 3) for k in ("load_plan_s", "feed_setup_s", "run_feed_s", "lines_s", "gather_s", "srt_s")})
     per_rank = [mine]
     if world > 1:
         bucket = [None] * world
@@ -608,7 +611,7 @@ def run_videos(args, rank, local_rank, world):
               "e2e": {"value": total * args.steps / wall_max, "unit": UNIT, "note": "the job IS end to end: frames come from the "
                       "video decoder through pinned host buffers, results go back to host text"},
               "per_rank": [{"rank": r, "frames_ocr": n, "s_per_step": round(w, 3), "feed_wait_s": round(fw, 3), "engine_s": round(es, 3),
-                            "frames_decoded": fd} for r, n, w, fw, es, fd in per_rank],
+                            "frames_decoded": fd, "phases_s": ph} for r, n, w, fw, es, fd, ph in per_rank],
               "limiter": "video decode (one cv2 decoder thread per rank)" if mine[3] > mine[4] else "engine",
               "gpu_launches": launches})
 

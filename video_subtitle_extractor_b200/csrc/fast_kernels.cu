@@ -395,7 +395,9 @@ __device__ __forceinline__ float2 fact2(float2 v) {
 }
 
 template <typename T, int K, int SH, int SW, int TH, int TW, int ACT>
-__global__ void __launch_bounds__(128, sizeof(T) == 2 ? 3 : 2) dwconv_reg_kernel(DwDev p, int tiles_x, int tiles_y) {
+// resident CTAs per SM (register caps 128 / 168 / 255): the kernel is latency bound (ncu: 0.46 eligible warps per scheduler at 8 warps
+// per SM, profiles/r02_ncu_summary.txt), so every variant takes the highest occupancy ptxas reaches without spilling
+__global__ void __launch_bounds__(128, K == 3 ? (SH * SW < 4 ? 4 : 3) : (sizeof(T) == 2 || SH * SW == 1) ? 3 : 2) dwconv_reg_kernel(DwDev p, int tiles_x, int tiles_y) {
     typedef PairOf<T> PR;
     constexpr int IH = (TH - 1) * SH + K, IW = (TW - 1) * SW + K;
     const int img = blockIdx.y;

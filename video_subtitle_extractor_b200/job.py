@@ -42,6 +42,21 @@ class Batch:
     ptrs: List[int] = field(default_factory=list)
 
 
+_PINNED_POOL: Dict[int, List[np.ndarray]] = {}   # slot index -> flat page-locked uint8 buffers, reused by successive feeds
+
+
+def _pinned_slot(index: int, shape) -> np.ndarray:
+    """Page-locked [batch, H, W, 3] view for ring slot `index`.  cudaHostAlloc of a 200 MB slot costs ~0.1 s and a job opens one
+    feed per video, so the flat buffers are kept and re-viewed (grown when a later video needs more bytes)."""
+    import torch                      # container for page-locked host memory only
+    need = int(np.prod(shape))
+    flat = _PINNED_POOL.get(index)
+    if flat is None or flat[0].size < need:
+        flat = [torch.empty((need,), dtype=torch.uint8, pin_memory=True).numpy()]
+        _PINNED_POOL[index] = flat
+    return flat[0][:need].reshape(shape)
+
+
 class FrameFeed:
     """Sequential batched decode of frames [first, last] (1-based, inclusive) of one video into pinned ring buffers.
 
@@ -65,8 +80,7 @@ class FrameFeed:
         self.slots = []
         for _ in range(slots):
             if pinned:
-                import torch                      # container for page-locked host memory only
-                self.slots.append(torch.empty((batch, self.h, self.w, 3), dtype=torch.uint8, pin_memory=True).numpy())
+                self.slots.append(_pinned_slot(len(self.slots), (batch, self.h, self.w, 3)))
             else:
                 self.slots.append(np.empty((batch, self.h, self.w, 3), np.uint8))
         self._free: "queue.Queue[int]" = queue.Queue()
@@ -220,6 +234,15 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
                   write_srt: bool = True, stats: Optional[dict] = None) -> JobResult:
     """Fast mode of the reference (`run` -> `extract_frame_by_fps`, backend/main.py:145-147) on this rank's share of the
     schedule.  `sub_area` 'default' = the reference's default area for the video's size; None = no area."""
+    import time
+    clock = [time.perf_counter()]
+
+    def lap(key):       # seconds since the previous lap, accumulated in stats[key]
+        now = time.perf_counter()
+        if stats is not None:
+            stats[key] = stats.get(key, 0.0) + now - clock[0]
+        clock[0] = now
+
     probe = FrameFeed(path, 1, 0, [], batch=1, slots=1, pinned=False)
     schedule = F.fast_mode_frames(probe.frame_count, probe.fps, extract_frequency)
     lo, hi = shard.frame_range(rank, world, len(schedule))
@@ -230,16 +253,21 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
     feed = None
     if mine:
         feed = FrameFeed(path, mine[0], mine[-1], mine, batch=batch, pinned=pinned, half=half)
+        lap("feed_setup_s")
         results = run_feed(engine, feed, stats=stats)
+    lap("run_feed_s")
     local = []
     for no in sorted(results):
         ls = rawtxt.lines_from_frame_result(no, results[no], characters, sub_area=sub_area, rec_char_type=rec_char_type,
                                             drop_score=drop_score)
         local.append((no, ls))
+    lap("lines_s")
     merged = shard.gather_by_frame(local)
     lines = [l for _, ls in merged for l in ls]
     msec = _gather_msec(feed)
+    lap("gather_s")
     subs, text = _srt(lines, probe.fps, path, threshold, msec) if write_srt else ([], "")
+    lap("srt_s")
     return JobResult(lines, subs, text, len(results), sorted(results), results)
 
 
