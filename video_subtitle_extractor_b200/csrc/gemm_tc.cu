@@ -43,7 +43,7 @@ static constexpr int kMaxSmem = 227 * 1024;
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
         stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems, split, kbb, out_bufs,
-        stack, acc_cols, tw_shift, tile_h;   // stack: see 'stacked split' (umma_kblock); acc_cols: TMEM columns per accumulator; spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
+        stack, acc_cols, kh_g, tw_shift, tile_h;   // kh_g: rowbox, vertical taps per A box;   // stack: see 'stacked split' (umma_kblock); acc_cols: TMEM columns per accumulator; spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
     void* out;
     int out_cs;
     const float* bias;
@@ -621,7 +621,7 @@ template <int MODE, int KH_, int KW_, bool TF32, bool SPLIT>
 __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full, uint64_t* empty, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, uint32_t a_lo0, uint32_t bres_lo,
                                               uint32_t stage16, int k_iters) {
-    const int KH = KH_ ? KH_ : p.kh, KW = KW_ ? KW_ : p.kw;
+    const int KH = KH_ ? KH_ : (MODE == 1 ? p.kh_g : p.kh), KW = KW_ ? KW_ : p.kw;
     // instruction descriptor: D = f32, A/B = f16 (kind::f16) or tf32 (kind::tf32, format code 2), N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | (TF32 ? (2u << 7) | (2u << 10) : 0u) | (uint32_t(p.n_chunk >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
     const uint32_t idesc2 = (SPLIT && p.stack) ? ((1u << 4) | (uint32_t((2 * p.n_chunk) >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24)) : 0u;
@@ -646,19 +646,22 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * p.acc_cols);
-        int kb = 0;
+        int kb = 0, kx1 = 0, ky0 = 0;                                // MODE 1: horizontal tap and first vertical tap of the box
         uint32_t b_it = bres_lo;                                     // resident slice of (k-iteration `it`)
         for (int it = 0; it < k_iters; it++) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const int ks = (kb == num_kb - 1) ? ks_last : 4;
-            const uint32_t b_first = resident ? b_it : a_lo + a16;
+            uint32_t b_first = resident ? b_it : a_lo + a16;
+            if constexpr (MODE == 1)     // iteration = (vertical-tap group, kx, k-block): first resident slice = tap (ky0, kx1)
+                if (resident) b_first = bres_lo + uint32_t((ky0 * p.kw + kx1) * num_kb + kb) * b_step;
             if (elect_one()) {
                 if constexpr (MODE == 0) {
                     umma_kblock<TF32, SPLIT>(d_tmem, a_lo, kDescHi, b_first, idesc, it != 0 ? 1u : 0u, ks, idesc2);
                 } else if constexpr (MODE == 1) {
+                    const int cnt = KH_ ? KH : min(KH, p.kh - ky0);    // KH = taps per box (p.kh_g); the last group may be short
 #pragma unroll
-                    for (int ky = 0; ky < KH; ky++) {
+                    for (int ky = 0; ky < cnt; ky++) {
                         const uint32_t a_t = a_lo + uint32_t(ky * 128);           // next image row of the box: 16 px * 128 B
                         const uint32_t b_t = b_first + uint32_t(ky) * b_ky_step;
                         umma_kblock<TF32, SPLIT>(d_tmem, a_t, kDescHi, b_t, idesc, (it | ky) != 0 ? 1u : 0u, ks, idesc2);
@@ -678,7 +681,11 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
             }
             __syncwarp();
             b_it += b_step;
-            if (++kb == num_kb) kb = 0;
+            if (++kb == num_kb) {
+                kb = 0;
+                if constexpr (MODE == 1)
+                    if (++kx1 == p.kw) { kx1 = 0; ky0 += KH; }
+            }
             a_lo += stage16;
             if (++stage == stages) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
         }
@@ -701,7 +708,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // halo (KxK, kernels up to 5x5): ONE box of (16 + kh - 1) x (8 + kw - 1) pixels per k-block serves every tap — the MMA
     // descriptors of tap (ky, kx) start (ky * box_w + kx) pixel rows into the box (tile = 16 rows x 8 columns, so that the
     // 8-row groups of the operand are one image row each, a uniform stride apart)
-    const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.halo ? p.kh * p.kw : p.rowbox ? p.kh : 1);
+    const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.halo ? p.kh * p.kw : p.rowbox ? p.kh_g : 1);
     const int stage_bytes = p.a_bytes + b_bytes;
     uint8_t* bres = smem + size_t(p.stages) * stage_bytes;          // resident weights: [tap][k-block][n_chunk x 64]
     uint8_t* sout = bres + p.b_total;                               // p.out_bufs staging tiles for the TMA stores
@@ -751,7 +758,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int total_tiles = p.num_m_tiles * p.n_chunks;
     const int taps = p.kh * p.kw;
-    const int k_iters = (p.halo ? 1 : p.rowbox ? p.kw : taps) * p.num_kb;
+    const int n_kg = p.rowbox ? (p.kh + p.kh_g - 1) / p.kh_g : 1;     // rowbox: groups of vertical taps, one A box each
+    const int k_iters = (p.halo ? 1 : p.rowbox ? p.kw * n_kg : taps) * p.num_kb;
 
     // Everything up to here (and the resident weight load below) touches only kernel parameters and static weights, so
     // under programmatic dependent launch (pdl.cuh) it overlaps the tail of the previous step's kernel; activations,
@@ -787,7 +795,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int it = 0; it < k_iters; it++) {
                     const int tap = it / p.num_kb, kb = it - tap * p.num_kb;   // rowbox: tap = kx
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], uint32_t(p.a_tx + b_bytes));
+                    int tx = p.a_tx + b_bytes;
+                    if (p.rowbox && !p.b_resident) tx = p.a_tx + min(p.kh_g, p.kh - (tap / p.kw) * p.kh_g) * p.n_chunk * 128;   // ragged last group
+                    mbar_expect_tx(&full[stage], uint32_t(tx));
                     uint8_t* a_dst = smem + size_t(stage) * stage_bytes;
                     if (p.halo) {
                         tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 - p.pw, y0 - p.ph, img);
@@ -795,10 +805,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * p.kbb,
                                         n_idx * p.n_chunk);
                     } else if (p.rowbox) {
-                        tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 + tap - p.pw, y0 - p.ph, img);
-                        for (int ky = 0; ky < p.kh && !p.b_resident; ky++)
-                            tma_load_2d(a_dst + p.a_bytes + ky * p.n_chunk * 128, &map_b, &full[stage],
-                                        (ky * p.kw + tap) * p.k_pad + kb * p.kbb, n_idx * p.n_chunk);
+                        // tap = gy * kw + kx: the box of vertical-tap group gy (taps ky0 .. ky0 + cnt - 1) at horizontal tap kx
+                        const int gy = tap / p.kw, kx = tap - gy * p.kw, ky0 = gy * p.kh_g, cnt = min(p.kh_g, p.kh - ky0);
+                        tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 + kx - p.pw, y0 - p.ph + ky0, img);
+                        for (int j = 0; j < cnt && !p.b_resident; j++)
+                            tma_load_2d(a_dst + p.a_bytes + j * p.n_chunk * 128, &map_b, &full[stage],
+                                        ((ky0 + j) * p.kw + kx) * p.k_pad + kb * p.kbb, n_idx * p.n_chunk);
                     } else {
                         if (p.spatial) {
                             const int ky = tap / p.kw, kx = tap - ky * p.kw;
@@ -831,7 +843,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.kh == 3 && p.kw == 3) VSE_MMA(2, 3, 3);
             else VSE_MMA(2, 0, 0);
         } else if (p.rowbox) {
-            if (p.kh == 3) VSE_MMA(1, 3, 0);
+            if (p.kh == 3 && p.kh_g == 3) VSE_MMA(1, 3, 0);
             else VSE_MMA(1, 0, 0);
         } else {
             VSE_MMA(0, 1, 1);
@@ -1093,10 +1105,21 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
         cuuint64_t strides[3] = {cuuint64_t(in_cs) * es, cuuint64_t(W) * in_cs * es, cuuint64_t(H) * W * in_cs * es};
         // rowbox: one box of 8 + kh - 1 rows per (kx, k-block) instead of one 8-row box per tap — kh x less L2->smem
         // traffic for the activations.  Needs >= 3 pipeline stages of (box + kh weight slices) in shared memory.
-        const int a_box = (8 + kh - 1) * 16 * 128;
-        const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + kh * w.n_chunk * 128);
-        t.rowbox = (!t.halo && t.tile_w == 16 && allow_rowbox && kh > 1 && 8 + kh - 1 <= 256 && rb_need <= kMaxSmem - slack - (w.split ? 2 : kOutBufs) * kOutBufBytes) ? 1 : 0;
-        cuuint32_t box[4] = {kbe, cuuint32_t(t.halo ? 8 + kw - 1 : t.tile_w), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + kh - 1 : t.tile_h), 1};
+        // Kernels too tall for that (9x9 with streamed weights: 9 weight slices per stage) split their vertical taps into equal
+        // groups of kh_g, one box of 8 + kh_g - 1 rows each: still kh_g x less activation traffic than per-tap boxes.
+        const int budget_rb = kMaxSmem - slack - (w.split ? 2 : kOutBufs) * kOutBufBytes;
+        t.kh_g = 0;
+        if (!t.halo && t.tile_w == 16 && allow_rowbox && kh > 1) {
+            for (int groups = 1; groups < kh && !t.kh_g; groups++) {
+                const int g = (kh + groups - 1) / groups;
+                if (g < 2) break;
+                const int a_box = (8 + g - 1) * 16 * 128;
+                const int rb_need = t.b_resident ? 3 * a_box + b_all : 3 * (a_box + g * w.n_chunk * 128);
+                if (rb_need <= budget_rb) t.kh_g = g;
+            }
+        }
+        t.rowbox = t.kh_g ? 1 : 0;
+        cuuint32_t box[4] = {kbe, cuuint32_t(t.halo ? 8 + kw - 1 : t.tile_w), cuuint32_t(t.halo ? 16 + kh - 1 : t.rowbox ? 8 + t.kh_g - 1 : t.tile_h), 1};
         err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box, a32);
     }
     if (!err.empty()) return err;
@@ -1160,7 +1183,7 @@ std::string launch_conv_tc_groups(TcConv* const* gs, const long long* pix_off, i
     bool changed = !*uploaded;
     for (int g = 0; g < n_groups; g++) {
         TcConv& t = *gs[g];
-        if (!t.spatial || t.halo != gs[0]->halo || t.rowbox != gs[0]->rowbox || t.tile_w != gs[0]->tile_w || t.b_resident != gs[0]->b_resident || t.num_kb != gs[0]->num_kb)
+        if (!t.spatial || t.halo != gs[0]->halo || t.rowbox != gs[0]->rowbox || t.kh_g != gs[0]->kh_g || t.tile_w != gs[0]->tile_w || t.b_resident != gs[0]->b_resident || t.num_kb != gs[0]->num_kb)
             return "groups with different kernel shapes";
         if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (of32 ? 3 : 7))) return "output view not 16-byte aligned";
         std::string err = tc_output_map(t, &changed);
@@ -1205,17 +1228,18 @@ static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const C
     p.stack = t.stack;
     p.acc_cols = t.n_chunk * (t.stack ? 2 : 1);
     p.rowbox = t.rowbox;
+    p.kh_g = t.rowbox ? t.kh_g : 0;
     p.halo = t.halo;
     p.tile_h = t.tile_h;
     p.tw_shift = t.tile_w == 8 ? 3 : t.tile_w == 16 ? 4 : 7;
-    p.a_tx = t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh - 1) * 16 * 128 : A_BYTES;
+    p.a_tx = t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh_g - 1) * 16 * 128 : A_BYTES;
     p.a_bytes = round_up_i(p.a_tx, 1024);
     p.n_total = t.n_chunk * t.n_chunks;
     p.param_smem = p.n_total <= kParamSmemMaxCh ? 1 : 0;
     const int param_bytes = p.param_smem ? 3 * p.n_total * int(sizeof(float)) : 0;
     p.b_resident = t.b_resident;
     p.b_total = t.b_resident ? t.kh * t.kw * t.num_kb * t.n_chunk * 128 : 0;
-    const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.halo ? t.kh * t.kw : t.rowbox ? t.kh : 1));
+    const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.halo ? t.kh * t.kw : t.rowbox ? t.kh_g : 1));
     // staging ring of the TMA stores: 4 tiles; split mode (operand stages and weights are twice the bytes) gives tiles back
     // to the operand pipeline until it holds 3 stages
     p.out_bufs = kOutBufs;

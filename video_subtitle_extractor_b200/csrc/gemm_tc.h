@@ -49,7 +49,8 @@ struct TcConv {
     int tile_w = 16, tile_h = 8;   // spatial tile (128 pixels): 8 x 16 halo, 16 x 8, 128 x 1 for maps of height 1
     int kh = 1, kw = 1, ph = 0, pw = 0;
     int cin = 0;            // real input channels (the MMA loop skips the all-zero tail of the last K block)
-    int rowbox = 0;         // KxK: A boxes span 8 + kh - 1 image rows and serve all vertical taps (see gemm_tc.cu)
+    int rowbox = 0;         // KxK: A boxes span 8 + kh_g - 1 image rows and serve kh_g vertical taps (see gemm_tc.cu)
+    int kh_g = 0;           // rowbox: vertical taps per box (= kh when everything fits; 9x9 kernels with streamed weights: 3)
     int tf32 = 0;           // fp32 activations / weights through kind::tf32 MMAs, fp32 output
     int split = 0;          // fp32 activations split in place into fp16 hi | lo, three kind::f16 MMAs per product, fp32 output
     float w_scale = 1.f;
