@@ -596,18 +596,19 @@ template <bool TF32, bool SPLIT>
 __device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a, uint32_t a_hi, uint32_t b, uint32_t idesc, uint32_t acc_first, int ks,
                                             uint32_t idesc2 = 0) {
     if constexpr (SPLIT) {
+        // ks = 1: the k-block holds at most 16 real channels (K tail) — the second K = 16 slice of hi and of lo is all zero
         if (idesc2 != 0) {
             umma_f16_words3(d_tmem, a, a_hi, b, kDescHi64, idesc2, acc_first);
-            umma_f16_words3(d_tmem, a + 2, a_hi, b + 2, kDescHi64, idesc2, 1u);
+            if (ks > 1) umma_f16_words3(d_tmem, a + 2, a_hi, b + 2, kDescHi64, idesc2, 1u);
             umma_f16_words3(d_tmem, a + 4, a_hi, b, kDescHi64, idesc, 1u);
-            umma_f16_words3(d_tmem, a + 6, a_hi, b + 2, kDescHi64, idesc, 1u);
+            if (ks > 1) umma_f16_words3(d_tmem, a + 6, a_hi, b + 2, kDescHi64, idesc, 1u);
         } else {
             umma_f16_words2(d_tmem, a, a_hi, b, idesc, acc_first);
-            umma_f16_words2(d_tmem, a + 2, a_hi, b + 2, idesc, 1u);
+            if (ks > 1) umma_f16_words2(d_tmem, a + 2, a_hi, b + 2, idesc, 1u);
             umma_f16_words2(d_tmem, a + 4, a_hi, b, idesc, 1u);
-            umma_f16_words2(d_tmem, a + 6, a_hi, b + 2, idesc, 1u);
+            if (ks > 1) umma_f16_words2(d_tmem, a + 6, a_hi, b + 2, idesc, 1u);
             umma_f16_words2(d_tmem, a, a_hi, b + 4, idesc, 1u);
-            umma_f16_words2(d_tmem, a + 2, a_hi, b + 6, idesc, 1u);
+            if (ks > 1) umma_f16_words2(d_tmem, a + 2, a_hi, b + 6, idesc, 1u);
         }
     } else {
         umma_words<TF32>(d_tmem, a, a_hi, b, idesc, acc_first);
@@ -631,7 +632,8 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
     const uint32_t b_step = uint32_t(n_chunk * 8);                  // one [n_chunk x 64] weight slice in 16-byte units
     const uint32_t a16 = uint32_t(p.a_bytes >> 4);
     const int umma_k = p.kb_elems / 4;   // K elements per MMA (32 bytes): 16 halves or 8 floats
-    const int ks_last = SPLIT ? 4 : min(4, (p.cin - (num_kb - 1) * p.kb_elems + umma_k - 1) / umma_k);   // all-zero K tail skipped
+    // all-zero K tail skipped (split: 32 channels per k-block = two K = 16 slices of hi and of lo; ks 4 stands for 'both')
+    const int ks_last = SPLIT ? ((p.cin - (num_kb - 1) * 32) <= 16 ? 1 : 4) : min(4, (p.cin - (num_kb - 1) * p.kb_elems + umma_k - 1) / umma_k);
     // strides between the weight slices of consecutive taps
     const uint32_t b_ky_step = resident ? uint32_t(KW * num_kb) * b_step : b_step;     // MODE 1
     const uint32_t b_tap_step = resident ? uint32_t(num_kb) * b_step : b_step;         // MODE 2
@@ -942,8 +944,9 @@ TcWeights tc_pack_weights(const float* w, int cout, int cin, int taps, int mode)
         t.n_chunks = (n_mma + 255) / 256;
         t.n_chunk = round_up_i((n_mma + t.n_chunks - 1) / t.n_chunks, t.n_chunks > 1 ? 64 : 16);
         const int num_kb = (cin + 31) / 32;
-        // narrow K-heavy layers (the 3x3 96 -> 24 convolutions of the FPN): hi / lo stacked along N, see umma_kblock
-        t.stack = (t.n_chunks == 1 && t.n_chunk <= 32 && taps * cin >= 256 && !getenv("VSE_NO_STACK")) ? 1 : 0;
+        // narrow K-heavy layers (the 3x3 96 -> 24 convolutions of the FPN, the 9x9 / 3x3 64-channel convolutions of the server
+        // detector, the recogniser's 1x3 480 -> 60 convolutions): hi / lo stacked along N, see umma_kblock
+        t.stack = (t.n_chunks == 1 && ((t.n_chunk <= 32 && taps * cin >= 256) || (t.n_chunk <= 64 && taps * cin >= 512)) && !getenv("VSE_NO_STACK")) ? 1 : 0;
         t.k_pad = num_kb * (t.stack ? 32 : 64);    // columns (halves) per tap
         t.taps = taps;
         const size_t rows = size_t(t.n_chunks) * t.n_chunk * (t.stack ? 2 : 1), cols = size_t(taps) * t.k_pad;
