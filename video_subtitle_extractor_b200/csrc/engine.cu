@@ -553,8 +553,12 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
         const StepRec& s = pd.steps[k];
         if (s.op != OP_CONV || lp.tcw[k].n_chunk == 0) continue;
         const ValueRec& vo = pd.values[s.out];
-        if (vo.dtype == DT_F32 || s.ins[0] == pd.hdr.input_vid) continue;
         const int kh = s.p[P_KH], kw = s.p[P_KW], ph = s.p[P_PH], pw = s.p[P_PW];
+        // fetched fp32 outputs are dense [pixels][channels]: only the single-channel map of a 1x1 head (V4/ch_det's last
+        // convolution) is taken, in the fp32 tensor-core mode, through the kernel's direct-store epilogue
+        const bool direct1 = vo.dtype == DT_F32 && vo.kind == KIND_IMG && s.p[P_COUT] == 1 && kh == 1 && kw == 1 && ph == 0 && pw == 0 &&
+                             plan_prec_[which] == VSE_PRECISION_FP32_TC && !s.p[P_HAS_RES];
+        if ((vo.dtype == DT_F32 && !direct1) || s.ins[0] == pd.hdr.input_vid) continue;
         const Geo& gi = cx.geos[cx.vals[s.ins[0]].geo];
         const bool flat = kh == 1 && kw == 1 && ph == 0 && pw == 0;
         bool uniform = true;
@@ -598,6 +602,7 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
                                         !(cfg.flags & VSE_FLAG_NO_HALO));
         if (!why.empty()) cx.tc[k].valid = false;
         cx.tc[k].a_scale = lp.a_scale[k];
+        cx.tc[k].direct1 = direct1 ? 1 : 0;
     }
     // transposed convolutions: four spatial 1x1 launches over the (uniform) input geometry
     cx.tc_dc.assign(pd.steps.size() * 4, TcConv{});

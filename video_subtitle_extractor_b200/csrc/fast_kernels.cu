@@ -557,7 +557,8 @@ bool launch_dwconv_reg(const ConvArgs& a, int max_out_h, int max_out_w, cudaStre
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem: 3x3 stride 2 pad 1, uint8 BGRX -> 16 channels, (x * nscale + nshift) fused into the load
+// stem: 3x3 stride 2 pad 1, uint8 BGRX -> 16 channels per blockIdx.z (the server detector's stem has 64: four channel blocks
+// re-read the small u8 input from L2), (x * nscale + nshift) fused into the load
 // ------------------------------------------------------------------------------------------------
 struct StemDev {
     const unsigned char* in; __half* out; const float* w; const float* bias; const ImgTab* tin; const ImgTab* tout;
@@ -571,11 +572,12 @@ __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
     pdl_trigger();
     __shared__ __align__(16) float sw[27 * 16];   // [(ky*3+kx)*3 + ci][co]
     __shared__ float sb[16];
+    const int co_base = blockIdx.z * 16;
     for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) {
         const int co = i & 15, r = i >> 4, ci = r % 3, tap = r / 3;
-        sw[i] = p.w[(size_t(tap) * p.w_ci + ci) * p.w_co + co];
+        sw[i] = p.w[(size_t(tap) * p.w_ci + ci) * p.w_co + co_base + co];
     }
-    if (threadIdx.x < 16) sb[threadIdx.x] = p.bias[threadIdx.x];
+    if (threadIdx.x < 16) sb[threadIdx.x] = p.bias[co_base + threadIdx.x];
     __syncthreads();
     const int img = blockIdx.y;
     const ImgTab ti = p.tin[img], to = p.tout[img];
@@ -640,18 +642,18 @@ __global__ void __launch_bounds__(128) stem_fast_kernel(StemDev p) {
             v[2 * j] = fact<ACT>(acc[t][j].x);
             v[2 * j + 1] = fact<ACT>(acc[t][j].y);
         }
-        T* o = reinterpret_cast<T*>(p.out) + (size_t(to.off) + size_t(oy) * to.w + ox) * p.out_cs;
+        T* o = reinterpret_cast<T*>(p.out) + (size_t(to.off) + size_t(oy) * to.w + ox) * p.out_cs + co_base;
         store8<T>(o, v);
         store8<T>(o + 8, v + 8);
     }
 }
 
 bool launch_stem_fast(const ConvArgs& a, int cout, int max_out_pix_pairs, cudaStream_t st, int prec) {
-    if (!a.in_u8 || a.kh != 3 || a.kw != 3 || a.sh != 2 || a.sw != 2 || a.ph != 1 || a.pw != 1 || cout != 16 || a.out_f32) return false;
-    if (a.epi.res || a.epi.post_scale || a.epi.act2 != ACT_NONE || !a.epi.bias || a.out_cs < 16) return false;
+    if (!a.in_u8 || a.kh != 3 || a.kw != 3 || a.sh != 2 || a.sw != 2 || a.ph != 1 || a.pw != 1 || cout % 16 || cout > 256 || a.out_f32) return false;
+    if (a.epi.res || a.epi.post_scale || a.epi.act2 != ACT_NONE || !a.epi.bias || a.out_cs < cout) return false;
     StemDev d{static_cast<const unsigned char*>(a.in), static_cast<__half*>(a.out), a.w, a.epi.bias, a.tin, a.tout,
               a.out_cs, a.w_ci, a.w_co, a.epi.act, {a.nscale[0], a.nscale[1], a.nscale[2]}, {a.nshift[0], a.nshift[1], a.nshift[2]}};
-    dim3 grid(cdiv_i(max_out_pix_pairs, 128), a.n_img);
+    dim3 grid(cdiv_i(max_out_pix_pairs, 128), a.n_img, cout / 16);
     if (prec == 1) {
         switch (a.epi.act) {
             case ACT_NONE: pdl_launch(stem_fast_kernel<float, ACT_NONE>, grid, 128, 0, st, d); return true;

@@ -43,7 +43,7 @@ static constexpr int kMaxSmem = 227 * 1024;
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
         stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems, split, kbb, out_bufs,
-        stack, acc_cols, kh_g, tw_shift, tile_h;   // kh_g: rowbox, vertical taps per A box;   // stack: see 'stacked split' (umma_kblock); acc_cols: TMEM columns per accumulator; spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
+        stack, acc_cols, kh_g, direct1, tw_shift, tile_h;   // kh_g: rowbox, vertical taps per A box;   // stack: see 'stacked split' (umma_kblock); acc_cols: TMEM columns per accumulator; spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
     void* out;
     int out_cs;
     const float* bias;
@@ -490,8 +490,12 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                     }
                     uint4 o[4];
                     epi_chunk16<ACT, POST, true, PSM, GATE>(e, raw0, ch0 + c0, pix, o, grow);
+                    if (p.direct1) {    // one dense fp32 channel: lane = pixel, a warp writes 128 contiguous bytes
+                        if (pix >= 0) static_cast<float*>(p.out)[pix * p.out_cs] = __uint_as_float(o[0].x);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) st_shared_16(buf + uint32_t(((j0 + j) ^ (row & 7)) << 4), o[j]);
+                        for (int j = 0; j < 4; j++) st_shared_16(buf + uint32_t(((j0 + j) ^ (row & 7)) << 4), o[j]);
+                    }
                 } else {
                     const bool two = c0 + 16 < p.n_chunk && ch0 + c0 + 16 < p.n_store;
                     uint32_t raw0[16], raw1[16];
@@ -510,6 +514,7 @@ __device__ __noinline__ void epilogue_loop(const TcParams& p, const CUtensorMap*
                 }
                 fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA store
             }
+            if (p.direct1) continue;                                    // (warp-uniform) nothing staged, nothing for TMA
             epi_barrier();
             if (issuer) {
                 const void* src = sout + size_t(slot) * kOutBufBytes;
@@ -1166,6 +1171,11 @@ static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const C
 
 std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st) {
     const bool of32 = t.tf32 || t.split;
+    if (t.direct1) {
+        if (!of32 || t.spatial || t.pack || t.n_store != 1 || t.n_chunks != 1) return "direct single-channel output needs a flat fp32 convolution";
+        t.map_o = t.map_a;      // never used for a store; the kernel only prefetches the descriptor
+        return launch_impl(t, sm_count, st, nullptr, nullptr, 0, t.num_m_tiles);
+    }
     if ((reinterpret_cast<uintptr_t>(t.out) & 15) || (t.out_cs & (of32 ? 3 : 7))) return "output view not 16-byte aligned";
     {
         std::string err = tc_output_map(t);
@@ -1229,6 +1239,7 @@ static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const C
     p.kb_elems = of32 ? 32 : BLOCK_K;              // activation elements per k-block
     p.kbb = t.split ? (t.stack ? 32 : 64) : p.kb_elems;   // weight columns per k-block
     p.stack = t.stack;
+    p.direct1 = t.direct1;
     p.acc_cols = t.n_chunk * (t.stack ? 2 : 1);
     p.rowbox = t.rowbox;
     p.kh_g = t.rowbox ? t.kh_g : 0;

@@ -57,6 +57,8 @@ struct TcConv {
     int stack = 0;          // split with hi / lo weights stacked along N (TcWeights::stack)
     float a_scale = 0.f;    // split: power of two for the operand rows (0 = the default of tc_split_activation_scale())
     int pack = 0;           // >0: pixel-packed flat conv (rows of `pack` pixels)
+    int direct1 = 0;        // flat fp32 convolution with ONE output channel stored densely (a probability map): the epilogue writes
+                            // out[pixel * out_cs] itself — a 4-byte pixel pitch is not addressable by a TMA store
     int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
     int halo = 0;           // KxK: one (16 + kh - 1) x (8 + kw - 1) box per k-block serves every tap (see gemm_tc.cu)
     int num_kb = 1;         // 64-channel K blocks per tap
