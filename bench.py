@@ -246,7 +246,7 @@ def run_reference(args, rank, world):
 def step_roofline(eng, E):
     """Per-kernel achieved HBM GB/s of the dominant kernel, from CUDA events between plan steps (engine stream)."""
     from video_subtitle_extractor_b200 import plan as P
-    rows, rows_out = [], []
+    rows, rows_out, rows_op = [], [], []
     for which in (E.PLAN_DET, E.PLAN_REC):
         try:
             ms, info = eng.debug_time_steps(which, reps=5)
@@ -257,7 +257,7 @@ def step_roofline(eng, E):
             op, kind = opk & 0xFF, opk >> 8
             if kind == 3:          # ran inside the previous step's fused kernel: fold its output bytes into that row
                 w_, n_, t_, b_, f_ = rows[-1]
-                if n_ == "conv_tc_kernel":
+                if n_ == "conv_tc_kernel" and rows_op[-1] != P.OP_DWCONV:
                     # a 1x1 conv heading a fused squeeze-excite group: the step's time covers three launches (pool of the conv
                     # input, gate, conv with the gate in its epilogue) — kept apart from the plain conv launches
                     n_ = "se_conv_group(conv_tc+gpool+gate)"
@@ -285,7 +285,9 @@ def step_roofline(eng, E):
             elif op == P.OP_DWCONV:
                 # the engine's default depthwise family is the register-tiled kernel (engine.cu, VSE_DW_MODE switches it)
                 dw_fast = {"0": "dwconv_fast_kernel", "1": "dwconv_tile_kernel"}.get(os.environ.get("VSE_DW_MODE", "2"), "dwconv_reg_kernel")
-                kname = dw_fast if kind == 2 else "dwconv_kernel"
+                # kind 1: computed inside the following 1x1 convolution's tensor-core kernel (fused depthwise -> pointwise); the 1x1
+                # step follows as kind 3 and folds its output bytes, weights and FLOPs into this row
+                kname = "conv_tc_kernel" if kind == 1 else dw_fast if kind == 2 else "dwconv_kernel"
             elif op == P.OP_DECONV2:
                 kname = "db_head_fused_kernel" if kind == 2 else ("conv_tc_kernel" if kind == 1 else "deconv2_kernel")
             elif op == P.OP_LSTM:
@@ -293,6 +295,7 @@ def step_roofline(eng, E):
             else:
                 kname = name.lower() + "_kernel"
             rows.append((which, kname, float(t), bytes_, flops))
+            rows_op.append(op)
             rows_out.append(out_bytes if op in (P.OP_CONV, P.OP_DWCONV, P.OP_DECONV2) else 0)
     if not rows:
         return None, []

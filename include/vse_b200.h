@@ -67,7 +67,11 @@ enum {
     /* the DETECTOR plan in VSE_PRECISION_FP32_TC whatever vse_config.precision says: with precision = VSE_PRECISION_FP16 the
      * recogniser keeps fp16 activations (its bar is CER <= 1e-3 on class ids, which fp16 meets on the reference's videos) while
      * the detector — whose 0.3 threshold crossing needs ~1e-5 on the probability map — keeps fp32 activations */
-    VSE_FLAG_DET_FP32_TC = 8192
+    VSE_FLAG_DET_FP32_TC = 8192,
+    /* opt-in experiment (fp32 tensor-core mode, equal-sized images): compute a stride-1 3x3 / 5x5 depthwise convolution inside the
+     * kernel of the 1x1 convolution that follows it (its output is never stored).  Bit-identical results, but measured SLOWER
+     * than the two separate kernels on B200 (the depthwise arithmetic gets 4 warps per SM instead of 16) */
+    VSE_FLAG_DWPW_FUSION = 16384
 };
 
 /* Mirrors the knobs the reference passes to PaddleOCR / TextDetector (ocr.py:91-113) and the

@@ -522,6 +522,49 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
             fd[ch.out] = k;
         }
     }
+    // Fused depthwise -> pointwise (opt-in: VSE_FLAG_DWPW_FUSION; fp32 tensor-core mode, equal-sized images): DWCONV (3x3 / 5x5,
+    // stride 1, same padding) whose only reader is the next step's 1x1 convolution.  The depthwise output is never allocated.
+    // Measured slower than the separate kernels, hence not the default.
+    cx.dwpw.assign(pd.steps.size(), 0);
+    if (!keep_all && plan_prec_[which] == VSE_PRECISION_FP32_TC && (cfg.flags & VSE_FLAG_DWPW_FUSION) &&
+        !(cfg.flags & (VSE_FLAG_NO_FAST_KERNELS | VSE_FLAG_NO_TENSOR_CORES))) {
+        auto readers = [&](int vid) {
+            int n = 0;
+            for (const StepRec& q : pd.steps)
+                for (int i = 0; i < 4; i++) n += q.ins[i] == vid;
+            return n;
+        };
+        for (int k = 0; k + 1 < nsteps; k++) {
+            const StepRec &dwc = pd.steps[k], &c = pd.steps[k + 1];
+            if (dwc.op != OP_DWCONV || c.op != OP_CONV || c.ins[0] != dwc.out || cx.se_conv[k + 1]) continue;
+            const int kd = dwc.p[P_KH];
+            if ((kd != 3 && kd != 5) || dwc.p[P_KW] != kd || dwc.p[P_SH] != 1 || dwc.p[P_SW] != 1 || dwc.p[P_PH] != kd / 2 || dwc.p[P_PW] != kd / 2) continue;
+            if (dwc.p[P_HAS_RES] || dwc.p[P_ACT2] != ACT_NONE || (dwc.p[P_ACT] != ACT_NONE && dwc.p[P_ACT] != ACT_RELU && dwc.p[P_ACT] != ACT_HSWISH)) continue;
+            if (c.p[P_KH] != 1 || c.p[P_KW] != 1 || c.p[P_SH] != 1 || c.p[P_SW] != 1 || c.p[P_PH] || c.p[P_PW]) continue;
+            const ValueRec &vd = pd.values[dwc.out], &vc = pd.values[c.out];
+            if (vd.alias_of >= 0 || vd.dtype != DT_ACT || vc.dtype != DT_ACT || readers(dwc.out) != 1 || dwc.ins[0] == pd.hdr.input_vid) continue;
+            if (lp.tcw[k + 1].n_chunk == 0 || lp.tcw[k + 1].n_chunks != 1 || lp.tcw[k + 1].stack || !lp.dev[k].bias || !lp.dev[k].w) continue;
+            bool is_out = false;
+            for (int i = 0; i < 4; i++) is_out = is_out || pd.hdr.output_vids[i] == dwc.out;
+            if (is_out) continue;
+            const Geo& g = cx.geos[cx.vals[dwc.ins[0]].geo];
+            bool uniform = !g.tab.empty();
+            for (auto& t : g.tab) uniform = uniform && t.h == g.tab[0].h && t.w == g.tab[0].w;
+            if (!uniform) continue;
+            // shared-memory budget (mirrors tc_conv_setup_dwpw)
+            const int nkb = (dwc.p[P_CIN] + 31) / 32, nck = lp.tcw[k + 1].n_chunk;
+            const int win = ((16 + kd - 1) * (8 + kd - 1) * 128 + 1023) / 1024 * 1024;
+            const int b_all = nkb * nck * 128;
+            const bool res = b_all <= 112 * 1024;
+            const int need = 2 * (win + 16384 + (res ? 0 : nck * 128)) + (res ? b_all : 0) + 2 * 16384 + (kd * kd + 3) * nkb * 128 + 3 * nck * 4 + 1536;
+            if (need > 227 * 1024) continue;
+            cx.dwpw[k] = 1;
+            fd[dwc.out] = -3;           // never materialised
+            // the fused kernel runs at the depthwise step: its output must be live BEFORE the depthwise input is released at the
+            // end of that step (allocated one step later it could land in the very memory the kernel is still reading)
+            fd[c.out] = std::min(fd[c.out], k);
+        }
+    }
     for (int k = -1; k <= nsteps; k++) {
         for (size_t v = 0; v < pd.values.size(); v++) {
             const ValueRec& r = pd.values[v];
@@ -597,6 +640,20 @@ void Engine::build_context(int which, const std::vector<ImgTab>& in_tab, bool ke
             if (why.empty()) continue;
         }
         const void* wdev = static_cast<const char*>(lp.tc_weights.p) + lp.tcw_off[k];
+        if (k > 0 && cx.dwpw[k - 1]) {
+            // fused depthwise -> pointwise: tensor maps over the DEPTHWISE input (ExecContext::dwpw)
+            const StepRec& dwc = pd.steps[k - 1];
+            const Geo& gd = cx.geos[cx.vals[dwc.ins[0]].geo];
+            TcConv& t = cx.tc[k];
+            std::string why = tc_conv_setup_dwpw(t, vptr(which, dwc.ins[0]), value_cs(pd, dwc.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], cx.n_img,
+                                                 gd.tab[0].h, gd.tab[0].w, dwc.p[P_KH]);
+            if (!why.empty()) throw StateError{"fused depthwise -> pointwise: " + why + " (clear VSE_FLAG_DWPW_FUSION)"};
+            t.dw_w = lp.dev[k - 1].w; t.dw_cp = pad8(dwc.p[P_CIN]); t.dw_bias = lp.dev[k - 1].bias; t.dw_act = dwc.p[P_ACT];
+            t.dw_ps = dwc.p[P_HAS_POST] ? lp.dev[k - 1].post_scale : nullptr;
+            t.dw_pt = dwc.p[P_HAS_POST] ? lp.dev[k - 1].post_shift : nullptr;
+            t.a_scale = lp.a_scale[k];
+            continue;
+        }
         std::string why = tc_conv_setup(cx.tc[k], vptr(which, s.ins[0]), value_cs(pd, s.ins[0]), s.p[P_CIN], wdev, lp.tcw[k], flat,
                                         gi.total, cx.n_img, gi.tab[0].h, gi.tab[0].w, kh, kw, ph, pw, !(cfg.flags & VSE_FLAG_NO_ROWBOX),
                                         !(cfg.flags & VSE_FLAG_NO_HALO));
@@ -824,7 +881,21 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                     for (const ImgTab& t : geo_of(s.out).tab) m = std::max(m, t.h * ((t.w + tw - 1) / tw));
                     return m;
                 };
-                if (s.op == OP_DWCONV) {
+                if (s.op == OP_DWCONV && cx.dwpw[k]) {
+                    // fused depthwise -> pointwise: the following 1x1 convolution's kernel computes this step on the fly
+                    const StepRec& c = pd.steps[k + 1];
+                    const StepDev& dc = lp.dev[k + 1];
+                    ConvArgs b;
+                    b.out = ptr_of(c.out);
+                    fill_epi(c, dc, b.epi);
+                    b.cout_store = pad8(c.p[P_COUT]);
+                    b.out_cs = value_cs(pd, c.out);
+                    if (!launch_conv(which, int(k + 1), b, prec)) throw StateError{"fused depthwise -> pointwise lost its tensor-core plan"};
+                    cx.kind[k] = 1;
+                    k++;
+                    cx.kind[k] = 3;
+                    if (step_events) cudaEventRecord((*step_events)[k], stream);
+                } else if (s.op == OP_DWCONV) {
                     if (out_f32) throw InvalidArg{"depthwise conv cannot produce a fetched output"};
                     // 0 strip, 1 shared-memory tiled, 2 (default) register tiled, 3 per layer: register tiled from
                     // VSE_DW_REG_MIN_C channels up, shared-memory tiled below

@@ -149,6 +149,9 @@ struct ExecContext {
     DevBuf tc_gdev;                 // per ragged step: the groups' tensor maps + geometry table on the device (gemm_tc.h)
     std::vector<size_t> tc_goff;    // byte offset of a step's table in tc_gdev
     std::vector<char> tc_gup;       // 1 = the table on the device is current
+    // per step: 1 = depthwise convolution computed inside the following 1x1 convolution's kernel (gemm_tc.h, TcConv::dw): the
+    // depthwise output is never materialised; the fused launch happens at the depthwise step, the 1x1 step is skipped
+    std::vector<char> dwpw;
     std::vector<char> se_conv; // per step: 1 = 1x1 conv heading a fused residual squeeze-excite group (build_context)
     std::vector<int> kind;    // per step, filled by exec_steps: which kernel family ran (see Engine::time_steps)
 };

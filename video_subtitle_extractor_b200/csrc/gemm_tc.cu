@@ -43,7 +43,7 @@ static constexpr int kMaxSmem = 227 * 1024;
 struct TcParams {
     int spatial, M, n_img, H, W, tiles_x, tiles_y, kh, kw, ph, pw, num_kb, k_pad, n_chunk, n_chunks, n_store, num_m_tiles,
         stages, tmem_cols, cin, rowbox, a_bytes, acc_stages, b_resident, b_total, halo, a_tx, tf32, kb_elems, split, kbb, out_bufs,
-        stack, acc_cols, kh_g, direct1, tw_shift, tile_h;   // kh_g: rowbox, vertical taps per A box;   // stack: see 'stacked split' (umma_kblock); acc_cols: TMEM columns per accumulator; spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
+        stack, acc_cols, kh_g, direct1, dw, dw_cp, dw_act, tw_shift, tile_h;   // dw: fused depthwise kernel size (0 = none)   // kh_g: rowbox, vertical taps per A box;   // stack: see 'stacked split' (umma_kblock); acc_cols: TMEM columns per accumulator; spatial tiles: 2^tw_shift columns x tile_h rows = 128 pixels (halo 8 x 16, default 16 x 8, text-line maps 128 x 1)
     void* out;
     int out_cs;
     const float* bias;
@@ -63,6 +63,7 @@ struct TcParams {
     int n_groups;
     int n_total;       // n_chunks * n_chunk (bias / post arrays are readable up to here)
     int param_smem;    // 1: bias/scale/shift staged in shared memory
+    const float *dw_w, *dw_bias, *dw_ps, *dw_pt;   // fused depthwise: [tap][dw_cp] filter, per-channel bias / post-affine (ps may be null)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -636,6 +637,8 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
     const bool resident = p.b_resident != 0;
     const uint32_t b_step = uint32_t(n_chunk * 8);                  // one [n_chunk x 64] weight slice in 16-byte units
     const uint32_t a16 = uint32_t(p.a_bytes >> 4);
+    const uint32_t op16 = p.dw ? a16 : 0u;                        // fused depthwise: the operand tile follows the input window
+    const uint32_t bo16 = a16 + (p.dw ? uint32_t(A_BYTES >> 4) : 0u);   // streamed weights follow the operand
     const int umma_k = p.kb_elems / 4;   // K elements per MMA (32 bytes): 16 halves or 8 floats
     // all-zero K tail skipped (split: 32 channels per k-block = two K = 16 slices of hi and of lo; ks 4 stands for 'both')
     const int ks_last = SPLIT ? ((p.cin - (num_kb - 1) * 32) <= 16 ? 1 : 4) : min(4, (p.cin - (num_kb - 1) * p.kb_elems + umma_k - 1) / umma_k);
@@ -659,12 +662,12 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const int ks = (kb == num_kb - 1) ? ks_last : 4;
-            uint32_t b_first = resident ? b_it : a_lo + a16;
+            uint32_t b_first = resident ? b_it : a_lo + bo16;
             if constexpr (MODE == 1)     // iteration = (vertical-tap group, kx, k-block): first resident slice = tap (ky0, kx1)
                 if (resident) b_first = bres_lo + uint32_t((ky0 * p.kw + kx1) * num_kb + kb) * b_step;
             if (elect_one()) {
                 if constexpr (MODE == 0) {
-                    umma_kblock<TF32, SPLIT>(d_tmem, a_lo, kDescHi, b_first, idesc, it != 0 ? 1u : 0u, ks, idesc2);
+                    umma_kblock<TF32, SPLIT>(d_tmem, a_lo + op16, kDescHi, b_first, idesc, it != 0 ? 1u : 0u, ks, idesc2);
                 } else if constexpr (MODE == 1) {
                     const int cnt = KH_ ? KH : min(KH, p.kh - ky0);    // KH = taps per box (p.kh_g); the last group may be short
 #pragma unroll
@@ -701,6 +704,75 @@ __device__ __forceinline__ void mma_warp_loop(const TcParams& p, uint64_t* full,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused depthwise -> pointwise: one operand stage.  The stage holds a (16 + K - 1) x (8 + K - 1) pixel window of the depthwise
+// INPUT (fp32 rows of 32 channels, 128B-swizzled by TMA; out-of-image pixels arrive as zeros = the convolution's padding).
+// The 128 threads of the transform warps compute the depthwise output of the 16 x 8 tile for these 32 channels and write it
+// as the [hi(32) | lo(32)] fp16 operand rows of the 1x1 convolution.  Thread t: channels 4q .. 4q + 3 (q = t & 7: one 16-byte
+// chunk; eight neighbouring lanes read one whole 128-byte pixel row, four rows per warp instruction: conflict free) of the
+// pixels r0 + 16 i (r0 = t >> 3, i < 8).  Accumulation per output: taps in (ky, kx) order, fmaf from 0, then + bias,
+// activation, post-affine — the arithmetic of dwconv_reg_kernel (fast_kernels.cu), so the fused path is bit-identical to it.
+// dwp: [K * K taps][C32] filter, then bias[C32], post scale[C32], post shift[C32] in shared memory (C32 = num_kb * 32).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __noinline__ void dw_operand_stage(const TcParams& p, uint32_t box, uint32_t opnd, const float* dwp, int kb, int t, float asc) {
+    constexpr int BW = 8 + K - 1;
+    const int q = t & 7, r0 = t >> 3;
+    const int C32 = p.num_kb * 32;
+    const uint32_t wq = smem_u32(dwp) + uint32_t(kb * 32 + 4 * q) * 4u;      // this thread's 4 channels of tap 0
+    auto ldw = [&](int row) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(wq + uint32_t(row * C32) * 4u));
+        return v;
+    };
+    const int px = r0 & 7, py0 = r0 >> 3;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll 1
+    for (int ky = 0; ky < K; ky++) {      // (not unrolled: the 25 x 8 window addresses of a 5x5 filter would all be kept in registers)
+#pragma unroll
+        for (int kx = 0; kx < K; kx++) {
+            const float4 w = ldw(ky * K + kx);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t row = uint32_t((py0 + 2 * i + ky) * BW + px + kx);
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                             : "r"(box + row * 128u + ((uint32_t(q) ^ (row & 7u)) << 4)));
+                acc[i][0] = fmaf(x.x, w.x, acc[i][0]); acc[i][1] = fmaf(x.y, w.y, acc[i][1]);
+                acc[i][2] = fmaf(x.z, w.z, acc[i][2]); acc[i][3] = fmaf(x.w, w.w, acc[i][3]);
+            }
+        }
+    }
+    const float4 b4 = ldw(K * K), s4 = ldw(K * K + 1), t4 = ldw(K * K + 2);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+    const bool post = p.dw_ps != nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t hi[2], lo[2];
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float x = __fadd_rn(acc[i][c], bb[c]);
+            if (p.dw_act == ACT_RELU) x = fmaxf(x, 0.f);
+            else if (p.dw_act == ACT_HSWISH)   // x * min(max(x + 3, 0), 6) * (1/6), left to right (fact2<ACT_HSWISH>)
+                x = __fmul_rn(__fmul_rn(x, fminf(fmaxf(__fadd_rn(x, 3.f), 0.f), 6.f)), 1.f / 6.f);
+            if (post) x = fmaf(x, ss[c], tt[c]);
+            v[c] = x * asc;
+        }
+        const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+        hi[0] = *reinterpret_cast<const uint32_t*>(&h0); hi[1] = *reinterpret_cast<const uint32_t*>(&h1);
+        lo[0] = *reinterpret_cast<const uint32_t*>(&l0); lo[1] = *reinterpret_cast<const uint32_t*>(&l1);
+        const uint32_t r = uint32_t(r0 + 16 * i);
+        const uint32_t rowa = opnd + r * 128u + uint32_t(q & 1) * 8u;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowa + ((uint32_t(q >> 1) ^ (r & 7u)) << 4)), "r"(hi[0]), "r"(hi[1]) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowa + ((uint32_t(4 + (q >> 1)) ^ (r & 7u)) << 4)), "r"(lo[0]), "r"(lo[1]) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 // SPLIT: the fp32-activation / 3-term fp16 product variant (p.split; 4 extra operand-transform warps).  A separate
@@ -716,7 +788,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // descriptors of tap (ky, kx) start (ky * box_w + kx) pixel rows into the box (tile = 16 rows x 8 columns, so that the
     // 8-row groups of the operand are one image row each, a uniform stride apart)
     const int b_bytes = p.b_resident ? 0 : p.n_chunk * 128 * (p.halo ? p.kh * p.kw : p.rowbox ? p.kh_g : 1);
-    const int stage_bytes = p.a_bytes + b_bytes;
+    const int opnd_bytes = p.dw ? A_BYTES : 0;                      // fused depthwise: the operand tile next to the input window
+    const int stage_bytes = p.a_bytes + opnd_bytes + b_bytes;
     uint8_t* bres = smem + size_t(p.stages) * stage_bytes;          // resident weights: [tap][k-block][n_chunk x 64]
     uint8_t* sout = bres + p.b_total;                               // p.out_bufs staging tiles for the TMA stores
     uint64_t* full = reinterpret_cast<uint64_t*>(sout + p.out_bufs * kOutBufBytes);
@@ -738,6 +811,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
         pb = sparam; ps = sparam + p.n_total; pt = sparam + 2 * p.n_total;
+    }
+    // fused depthwise: filter taps, bias and post-affine of all input channels, zero beyond the real channels
+    float* dwp = sparam + (p.param_smem ? 3 * p.n_total : 0);
+    if (p.dw) {
+        const int C32 = p.num_kb * 32, taps_dw = p.dw * p.dw;
+        for (int i = threadIdx.x; i < (taps_dw + 3) * C32; i += blockDim.x) {
+            const int r = i / C32, c = i - r * C32;
+            float v = 0.f;
+            if (c < p.cin) {
+                if (r < taps_dw) v = p.dw_w[size_t(r) * p.dw_cp + c];
+                else if (r == taps_dw) v = p.dw_bias[c];
+                else if (p.dw_ps) v = r == taps_dw + 1 ? p.dw_ps[c] : p.dw_pt[c];
+            }
+            dwp[i] = v;
+        }
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -806,7 +894,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (p.rowbox && !p.b_resident) tx = p.a_tx + min(p.kh_g, p.kh - (tap / p.kw) * p.kh_g) * p.n_chunk * 128;   // ragged last group
                     mbar_expect_tx(&full[stage], uint32_t(tx));
                     uint8_t* a_dst = smem + size_t(stage) * stage_bytes;
-                    if (p.halo) {
+                    if (p.dw) {
+                        // window of the depthwise input for this tile and k-block; the 1x1 weights follow the operand tile
+                        tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 - p.pw, y0 - p.ph, img);
+                        if (!p.b_resident)
+                            tma_load_2d(a_dst + p.a_bytes + opnd_bytes, &map_b, &full[stage], kb * p.kbb, n_idx * p.n_chunk);
+                    } else if (p.halo) {
                         tma_load_4d(a_dst, tg.ma, &full[stage], kb * p.kb_elems, x0 - p.pw, y0 - p.ph, img);
                         for (int tp = 0; tp < taps && !p.b_resident; tp++)
                             tma_load_2d(a_dst + p.a_bytes + tp * p.n_chunk * 128, &map_b, &full[stage], tp * p.k_pad + kb * p.kbb,
@@ -875,7 +968,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (long long it = 0; it < n_it; it++) {
             mbar_wait(&full[stage], phase);
             const uint32_t base = smem_u32(smem + size_t(stage) * stage_bytes);
-            for (int r = xt; r < rows; r += 32 * kXfWarps) {
+            if (p.dw) {
+                const int kb = int(it % p.num_kb);
+                if (p.dw == 3) dw_operand_stage<3>(p, base, base + uint32_t(p.a_bytes), dwp, kb, xt, asc);
+                else dw_operand_stage<5>(p, base, base + uint32_t(p.a_bytes), dwp, kb, xt, asc);
+            }
+            for (int r = xt; r < rows && !p.dw; r += 32 * kXfWarps) {
                 const uint32_t row = base + uint32_t(r) * 128u, sw = uint32_t(r & 7);
                 float4 v[8];
 #pragma unroll
@@ -1143,6 +1241,52 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
     return "";
 }
 
+std::string tc_conv_setup_dwpw(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, int n_img, int H, int W,
+                               int dw) {
+    t.valid = false;
+    if (!w.split || w.stack || w.n_chunks != 1 || w.taps != 1) return "fused depthwise needs a single-chunk split-mode 1x1 convolution";
+    if (dw != 3 && dw != 5) return "fused depthwise: 3x3 or 5x5 only";
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (in_cs & 3)) return "activation view not 16-byte aligned";
+    t.kh = t.kw = 1;
+    t.ph = t.pw = dw / 2;             // offsets of the input window (the depthwise padding)
+    t.dw = dw;
+    t.k_pad = w.k_pad;
+    t.cin = cin;
+    t.rowbox = 0; t.halo = 0; t.kh_g = 0; t.pack = 0; t.direct1 = 0;
+    t.tf32 = 0; t.split = 1; t.stack = 0;
+    t.w_scale = w.w_scale;
+    t.num_kb = (cin + 31) / 32;
+    t.n_chunk = w.n_chunk;
+    t.n_chunks = 1;
+    const int b_all = t.num_kb * w.n_chunk * 128;
+    t.b_resident = b_all <= kBResidentMaxSplit ? 1 : 0;
+    t.spatial = 1;
+    t.n_img = n_img; t.H = H; t.W = W;
+    t.tile_w = 8; t.tile_h = 16;
+    t.tiles_x = (W + 7) / 8;
+    t.tiles_y = (H + 15) / 16;
+    t.num_m_tiles = n_img * t.tiles_x * t.tiles_y;
+    // two stages of (window + operand tile + streamed weight slice) must fit next to the resident weights and two store tiles
+    const int win = round_up_i((16 + dw - 1) * (8 + dw - 1) * 128, 1024);
+    const int stage = win + A_BYTES + (t.b_resident ? 0 : w.n_chunk * 128);
+    const int dw_param = (dw * dw + 3) * t.num_kb * 32 * 4;
+    if (2 * stage + (t.b_resident ? b_all : 0) + 2 * kOutBufBytes + dw_param + 3 * w.n_chunk * 4 + 1024 + kBarRegion > kMaxSmem) return "fused depthwise: stages do not fit";
+    cuuint64_t dims[4] = {cuuint64_t(cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(n_img)};
+    cuuint64_t strides[3] = {cuuint64_t(in_cs) * 4, cuuint64_t(W) * in_cs * 4, cuuint64_t(H) * W * in_cs * 4};
+    cuuint32_t box[4] = {32, cuuint32_t(8 + dw - 1), cuuint32_t(16 + dw - 1), 1};
+    std::string err = encode(&t.map_a, const_cast<void*>(in), 4, dims, strides, box, true);
+    if (!err.empty()) return err;
+    {
+        cuuint64_t bdims[2] = {cuuint64_t(w.k_pad), cuuint64_t(w.n_chunk)};
+        cuuint64_t bstrides[1] = {cuuint64_t(w.k_pad) * 2};
+        cuuint32_t bbox[2] = {64, cuuint32_t(w.n_chunk)};
+        err = encode(&t.map_b, const_cast<void*>(wdev), 2, bdims, bstrides, bbox, false);
+        if (!err.empty()) return err;
+    }
+    t.valid = true;
+    return "";
+}
+
 // output tensor map (TMA stores): [n_store channels] x pixels, row pitch out_cs; re-encoded only when the target changes
 static std::string tc_output_map(TcConv& t, bool* changed = nullptr) {
     if (t.map_o_ptr == t.out && t.map_o_cs == t.out_cs && t.map_o_n == t.n_store) return "";
@@ -1246,14 +1390,17 @@ static std::string launch_impl(TcConv& t, int sm_count, cudaStream_t st, const C
     p.halo = t.halo;
     p.tile_h = t.tile_h;
     p.tw_shift = t.tile_w == 8 ? 3 : t.tile_w == 16 ? 4 : 7;
-    p.a_tx = t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh_g - 1) * 16 * 128 : A_BYTES;
+    p.a_tx = t.dw ? (16 + t.dw - 1) * (8 + t.dw - 1) * 128 : t.halo ? (16 + t.kh - 1) * (8 + t.kw - 1) * 128 : t.rowbox ? (8 + t.kh_g - 1) * 16 * 128 : A_BYTES;
+    p.dw = t.dw; p.dw_cp = t.dw_cp; p.dw_act = t.dw_act;
+    p.dw_w = t.dw_w; p.dw_bias = t.dw_bias; p.dw_ps = t.dw_ps; p.dw_pt = t.dw_pt;
+    if (t.dw && (!t.split || !t.dw_w || !t.dw_bias)) return "fused depthwise: parameters missing";
     p.a_bytes = round_up_i(p.a_tx, 1024);
     p.n_total = t.n_chunk * t.n_chunks;
     p.param_smem = p.n_total <= kParamSmemMaxCh ? 1 : 0;
-    const int param_bytes = p.param_smem ? 3 * p.n_total * int(sizeof(float)) : 0;
+    const int param_bytes = (p.param_smem ? 3 * p.n_total * int(sizeof(float)) : 0) + (t.dw ? (t.dw * t.dw + 3) * t.num_kb * 32 * int(sizeof(float)) : 0);
     p.b_resident = t.b_resident;
     p.b_total = t.b_resident ? t.kh * t.kw * t.num_kb * t.n_chunk * 128 : 0;
-    const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : t.n_chunk * 128 * (t.halo ? t.kh * t.kw : t.rowbox ? t.kh_g : 1));
+    const int stage_bytes = p.a_bytes + (t.dw ? A_BYTES : 0) + (p.b_resident ? 0 : t.n_chunk * 128 * (t.halo ? t.kh * t.kw : t.rowbox ? t.kh_g : 1));
     // staging ring of the TMA stores: 4 tiles; split mode (operand stages and weights are twice the bytes) gives tiles back
     // to the operand pipeline until it holds 3 stages
     p.out_bufs = kOutBufs;

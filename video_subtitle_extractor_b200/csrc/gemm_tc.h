@@ -57,6 +57,14 @@ struct TcConv {
     int stack = 0;          // split with hi / lo weights stacked along N (TcWeights::stack)
     float a_scale = 0.f;    // split: power of two for the operand rows (0 = the default of tc_split_activation_scale())
     int pack = 0;           // >0: pixel-packed flat conv (rows of `pack` pixels)
+    // Fused depthwise -> pointwise (split mode): the TMA boxes are (16 + dw - 1) x (8 + dw - 1) pixel windows of the DEPTHWISE
+    // convolution's input; the operand rows of the 1x1 convolution are computed from them in shared memory by the transform
+    // warps (depthwise taps, bias, activation, post-affine, then the hi | lo split).  dw = depthwise kernel size (0 = none)
+    int dw = 0, dw_cp = 0, dw_act = 0;       // dw_cp: channel pitch of the [tap][channel] depthwise filter
+    const float* dw_w = nullptr;
+    const float* dw_bias = nullptr;
+    const float* dw_ps = nullptr;            // optional post-affine of the depthwise step
+    const float* dw_pt = nullptr;
     int direct1 = 0;        // flat fp32 convolution with ONE output channel stored densely (a probability map): the epilogue writes
                             // out[pixel * out_cs] itself — a 4-byte pixel pitch is not addressable by a TMA store
     int b_resident = 0;     // the whole weight matrix stays in shared memory for the kernel's lifetime
@@ -83,6 +91,10 @@ std::string tc_conv_setup(TcConv& t, const void* in, int in_cs, int cin, const v
 
 // returns an empty string on success, else why the launch was not possible (nothing launched)
 std::string launch_conv_tc(TcConv& t, int sm_count, cudaStream_t st);
+// fused depthwise(dw x dw, stride 1, same padding) -> 1x1 convolution over equal-sized images, split mode only: `in` is the
+// DEPTHWISE input; the depthwise parameters go into t.dw_* before the launch (see TcConv::dw)
+std::string tc_conv_setup_dwpw(TcConv& t, const void* in, int in_cs, int cin, const void* wdev, const TcWeights& w, int n_img, int H, int W,
+                               int dw);
 
 // one group of a ragged launch as the kernel reads it
 struct TcGroupDev {

@@ -25,6 +25,7 @@ FLAG_NO_CONCAT_GATHER, FLAG_NO_HALO = 256, 512
 FLAG_DET_FP32, FLAG_DET_TF32 = 1024, 2048
 FLAG_NO_SE_CONV = 4096
 FLAG_DET_FP32_TC = 8192
+FLAG_DWPW_FUSION = 16384
 
 
 class VseConfig(C.Structure):
