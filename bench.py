@@ -348,6 +348,7 @@ def run_b200(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    numa = shard.bind_to_gpu_numa_node(local_rank) if world > 1 else None     # before any page-locked allocation
     if world > 1:
         import torch.distributed as dist
         # NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr: stdout carries the one JSON line only
@@ -458,7 +459,7 @@ def run_b200(args, rank, local_rank, world):
 
     wall_max = shard.max_over_ranks(wall, dev)
     wall_e2e_max = shard.max_over_ranks(wall_e2e, dev)
-    per_rank = [(rank, wall / args.steps * 1e3, dev_s / args.steps * 1e3, wall_e2e / args.steps * 1e3, n_lines / max(args.steps, 1))]
+    per_rank = [(rank, wall / args.steps * 1e3, dev_s / args.steps * 1e3, wall_e2e / args.steps * 1e3, n_lines / max(args.steps, 1), numa)]
     if world > 1:
         bucket = [None] * world
         torch.distributed.all_gather_object(bucket, per_rank[0])
@@ -518,7 +519,7 @@ def run_b200(args, rank, local_rank, world):
             "precision": prec_name + (f"; vse_config.flags={args.flags}" if args.flags else ""),
             "text_lines_per_frame": n_lines / max(args.steps * B, 1), "mean_padded_rec_width": mean_width,
             "per_rank": [{"rank": r, "ms_per_step": round(a, 4), "device_ms_per_step": round(b, 4), "e2e_ms_per_step": round(c, 4),
-                          "text_lines_per_step": d} for r, a, b, c, d in per_rank],
+                          "text_lines_per_step": d, "numa_node": nn} for r, a, b, c, d, nn in per_rank],
             "device_ms_per_step": dev_s / args.steps * 1e3, "stage_ms_last_e2e_step": stage_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_max / args.steps * 1e3, "device_ms_per_step": dev_s_e2e / args.steps * 1e3,
@@ -552,6 +553,7 @@ def run_videos(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
+        shard.bind_to_gpu_numa_node(local_rank)        # decode thread + page-locked ring next to the GPU
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=torch.device(dev))
     vids = os.path.join(ROOT, "tests", "golden", "_videos")

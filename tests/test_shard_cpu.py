@@ -53,3 +53,13 @@ def test_two_gloo_ranks_broadcast_and_merge(tmp_path):
     assert "rec-plan-bytes" in lines[0] and "rec-plan-bytes" in lines[1]
     assert "[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]" in lines[0] and "[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]" in lines[1]
     assert lines[0].rstrip().endswith("2.0") and lines[1].rstrip().endswith("2.0")
+
+
+def test_numa_binding_helpers_are_safe_without_a_gpu():
+    """bench.py binds every rank of a multi-GPU run to the CPUs next to its GPU before allocating page-locked buffers; where the
+    topology cannot be read (this container: no GPU) nothing changes."""
+    import os
+    assert shard._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    before = os.sched_getaffinity(0)
+    assert shard.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before

@@ -20,6 +20,62 @@ def frame_range(rank: int, world: int, n_frames: int) -> Tuple[int, int]:
     return rank * n_frames // world, (rank + 1) * n_frames // world
 
 
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device: int) -> Optional[int]:
+    """NUMA node the GPU's PCIe root hangs off (/sys/bus/pci/devices/<bdf>/numa_node), or None when it cannot be told."""
+    import os
+    import subprocess
+    bdf = None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception:
+        bdf = None
+    if bdf is None or not os.path.exists(f"/sys/bus/pci/devices/{bdf}/numa_node"):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+            bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1b:00.0 -> 0000:1b:00.0
+        except Exception:
+            return None
+    try:
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device: int) -> Optional[int]:
+    """Restrict this process to the CPUs of the GPU's NUMA node BEFORE it allocates page-locked frame buffers: first-touch then
+    places them in the memory next to the GPU's PCIe root, so that the eight concurrent host->device copies of an 8-GPU box do
+    not cross the socket interconnect (the end-to-end limiter at N = 8).  Returns the node, or None (nothing
+    changed) when the topology cannot be read or the node's CPUs are not available to this process."""
+    import os
+    node = gpu_numa_node(device)
+    if node is None or os.environ.get("VSE_NO_NUMA_BIND"):
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read()) & set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def _dist():
     import torch.distributed as dist
     return dist
