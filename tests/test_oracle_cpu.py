@@ -82,7 +82,10 @@ def test_graph_oracle_matches_survey_anchor():
 @needs_ref
 @pytest.mark.parametrize("name,shape", [("V4/ch_det_fast", (1, 3, 96, 160)), ("V4/en_rec_fast", (2, 3, 48, 336)),
                                         ("V4/ch_rec_fast", (1, 3, 48, 320)), ("V3/japan_rec_fast", (1, 3, 48, 320)),
-                                        ("V3/korean_rec_fast", (1, 3, 48, 328)), ("V2/ch_rec", (2, 3, 32, 168))])
+                                        ("V3/korean_rec_fast", (1, 3, 48, 328)), ("V2/ch_rec", (2, 3, 32, 168)),
+                                        # the accurate-mode (server) models: PP-HGNet + LK-PAN + PFHeadLocal (whose concat slices
+                                        # the plan compiler reorders, plan.py::_reorder_concats) and the 6625-class SVTR recogniser
+                                        ("V4/ch_det", (1, 3, 96, 128)), ("V4/ch_rec", (1, 3, 48, 160))])
 def test_compiled_plan_equals_shipped_graph(name, shape):
     from oracle.graph_interp import GraphInterpreter
     from oracle.plan_interp import PlanInterpreter
