@@ -713,6 +713,18 @@ const void* Engine::value_ptr(int which, int vid, int* cs, const Geo** geo) {
     return vptr(which, vid);
 }
 
+int Engine::logits_vid(int which) const {
+    const LoadedPlan& lp = plans_[which];
+    if (!lp.loaded || lp.data.steps.empty() || plan_prec_[which] == VSE_PRECISION_FP16 || (cfg.flags & VSE_FLAG_NO_FAST_KERNELS)) return -1;
+    const PlanData& pd = lp.data;
+    const StepRec& s = pd.steps.back();
+    if (s.op != OP_SOFTMAX || s.out != pd.hdr.output_vids[0] || s.ins[0] < 0 || pd.values[s.ins[0]].dtype != DT_ACT) return -1;
+    int readers = 0;
+    for (const StepRec& q : pd.steps)
+        for (int i = 0; i < 4; i++) readers += q.ins[i] == s.ins[0];
+    return readers == 1 ? s.ins[0] : -1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // execution
 // ------------------------------------------------------------------------------------------------
@@ -1118,6 +1130,10 @@ void Engine::exec_steps(int which, std::vector<cudaEvent_t>* step_events) {
                 break;
             }
             case OP_SOFTMAX: {
+                if (fold_final_softmax && !last_keep_all_[which] && k + 1 == pd.steps.size() && logits_vid(which) == s.ins[0]) {
+                    cx.kind[k] = 3;      // the CTC decode works on the logits (Engine::fold_final_softmax)
+                    break;
+                }
                 launch_softmax(ptr_of(s.ins[0]), value_cs(pd, s.ins[0]), static_cast<float*>(ptr_of(s.out)), vo.channels,
                                geo_of(s.out).total, prec, stream);
                 launches++;
@@ -1150,6 +1166,8 @@ int Engine::time_steps(int which, int reps, float* ms, int64_t* info, int cap) {
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) VSE_CUDA(cudaEventCreate(&e));
     std::vector<double> acc(n, 0.0);
+    struct FoldGuard { bool& f; bool old; ~FoldGuard() { f = old; } } fold_guard{fold_final_softmax, fold_final_softmax};
+    fold_final_softmax = which == VSE_PLAN_REC;     // what run_frames does
     exec_steps(which);  // warm
     VSE_CUDA(cudaStreamSynchronize(stream));
     for (int r = 0; r < reps; r++) {

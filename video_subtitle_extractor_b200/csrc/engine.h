@@ -195,6 +195,11 @@ class Engine {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     int64_t tc_launches = 0;
+    // Recogniser plans end in SOFTMAX over the class logits, whose only reader is the CTC decode: run_frames decodes straight from
+    // the logits (postproc.cu, ctc_decode_kernel) and exec_steps skips the step while this is set.  logits_vid(): the value that
+    // feeds that SOFTMAX when the fold applies to the loaded plan (float activations, single reader), else -1
+    bool fold_final_softmax = false;
+    int logits_vid(int which) const;
 
   private:
     void prepare_plan(int which, LoadedPlan& lp);

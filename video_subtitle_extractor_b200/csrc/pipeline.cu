@@ -530,16 +530,23 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
     }
     VSE_CUDA(cudaEventRecord(P->ev[5], stream));
 
-    // 6. recogniser network on the ragged batch
-    run_plan(VSE_PLAN_REC, rec_tab, P->rec_in.as<uint8_t>(), false);
+    // 6. recogniser network on the ragged batch (its final softmax is folded into the CTC decode when the plan allows it)
+    {
+        struct FoldGuard { bool& f; ~FoldGuard() { f = false; } } fold_guard{fold_final_softmax};
+        fold_final_softmax = true;
+        run_plan(VSE_PLAN_REC, rec_tab, P->rec_in.as<uint8_t>(), false);
+    }
     VSE_CUDA(cudaEventRecord(P->ev[6], stream));
 
     // 7. CTC greedy decode + results
     {
         const int rec_vid = plans_[1].data.hdr.output_vids[0];
-        int C = 0;
+        const int lg_vid = logits_vid(VSE_PLAN_REC);      // >= 0: the softmax step was skipped, decode from the logits
+        int C = 0, cs = 0;
         const Geo* rg = nullptr;
         const float* probs = static_cast<const float*>(value_ptr(VSE_PLAN_REC, rec_vid, &C, &rg));
+        cs = C;
+        if (lg_vid >= 0) probs = static_cast<const float*>(value_ptr(VSE_PLAN_REC, lg_vid, &cs, nullptr));
         if (!rg) throw InvalidArg{"recognition plan output has no geometry"};
         int max_t = 1;
         std::vector<int> meta(2 * nC);
@@ -555,7 +562,7 @@ void Engine::run_frames(const uint8_t* const* frames, const int32_t* h, const in
         P->h_in.reserve(meta.size() * sizeof(int));
         std::memcpy(P->h_in.p, meta.data(), meta.size() * sizeof(int));
         launch_upload(P->ctc_meta.p, P->h_in.p, meta.size() * sizeof(int), stream);
-        launch_ctc_decode(probs, C, P->ctc_meta.as<int>(), P->ctc_meta.as<int>() + nC, nC, max_t, P->ctc_ids.as<int>(),
+        launch_ctc_decode(probs, C, cs, lg_vid >= 0, P->ctc_meta.as<int>(), P->ctc_meta.as<int>() + nC, nC, max_t, P->ctc_ids.as<int>(),
                           P->ctc_len.as<int>(), P->ctc_score.as<float>(), stream);
         launches++;
         VSE_CUDA(cudaGetLastError());

@@ -534,11 +534,14 @@ void launch_crops(const CropJob* jobs_dev, int n_jobs, int max_pix, const short*
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTC greedy decode: argmax/max per time step, collapse repeats, drop blank (0), mean of kept max-probs
+// CTC greedy decode: argmax/max per time step, collapse repeats, drop blank (0), mean of kept max-probs.
+// logits != 0: the rows are the class LOGITS of the recogniser head (row pitch cs), the plan's final softmax is not run at all —
+// argmax is the same, and the probability of the winning class is 1 / sum_c exp(x_c - max) (one online pass:
+// running maximum and rescaled sum per lane, merged over the warp), so the normalised [T, C] matrix never exists in HBM.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict__ probs, int C, const int* __restrict__ toff,
-                                                         const int* __restrict__ tlen, int max_t, int* __restrict__ ids,
-                                                         int* __restrict__ id_len, float* __restrict__ score) {
+__global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict__ probs, int C, int cs, int logits,
+                                                         const int* __restrict__ toff, const int* __restrict__ tlen, int max_t,
+                                                         int* __restrict__ ids, int* __restrict__ id_len, float* __restrict__ score) {
     pdl_wait();      // pdl.cuh: nothing below may run before the previous kernel of the stream has completed
     pdl_trigger();
     __shared__ int bad;
@@ -549,26 +552,42 @@ __global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict
     float* bp = reinterpret_cast<float*>(bi + max_t);
     const int n = blockIdx.x;
     const int T = tlen[n];
-    const float* base = probs + size_t(toff[n]) * C;
+    const float* base = probs + size_t(toff[n]) * cs;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int t = warp; t < T; t += 4) {
-        const float* row = base + size_t(t) * C;
-        float best = -FLT_MAX;
+        const float* row = base + size_t(t) * cs;
+        float best = -FLT_MAX, sum = 0.f;       // sum: sum of exp(x - best) over this lane's classes (logits mode)
         int idx = 0x7fffffff;
         bool nonfinite = false;
         for (int c = lane; c < C; c += 32) {
             const float v = row[c];
             nonfinite |= !(fabsf(v) <= FLT_MAX);
-            if (v > best) { best = v; idx = c; }
+            if (v > best) {
+                if (logits) sum = sum * __expf(best - v) + 1.f;
+                best = v;
+                idx = c;
+            } else if (logits) {
+                sum += __expf(v - best);
+            }
         }
-        if (nonfinite) bad = 1;   // NaN / Inf in the class probabilities (fp16 overflow inside the recogniser plan)
+        if (nonfinite) bad = 1;   // NaN / Inf in the class scores (fp16 overflow inside the recogniser plan)
+        const float lane_best = best;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
         }
-        if (lane == 0) { bi[t] = idx < C ? idx : 0; bp[t] = best; }
+        if (logits) {
+            float s = idx == 0x7fffffff ? 0.f : sum * __expf(lane_best - best);   // lanes without a class (C < 32) hold best = -FLT_MAX, sum = 0
+            if (lane_best == -FLT_MAX) s = 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) { bi[t] = idx < C ? idx : 0; bp[t] = 1.f / s; }
+        } else if (lane == 0) {
+            bi[t] = idx < C ? idx : 0;
+            bp[t] = best;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -594,8 +613,8 @@ __global__ void __launch_bounds__(128) ctc_decode_kernel(const float* __restrict
     }
 }
 
-void launch_ctc_decode(const float* probs, int C, const int* toff, const int* tlen, int n, int max_t, int* ids, int* id_len,
-                       float* score, cudaStream_t st) {
+void launch_ctc_decode(const float* probs, int C, int cs, bool logits, const int* toff, const int* tlen, int n, int max_t, int* ids,
+                       int* id_len, float* score, cudaStream_t st) {
     if (n <= 0) return;
     size_t smem = size_t(max_t) * 8;
     if (smem > 48 * 1024) {
@@ -607,7 +626,7 @@ void launch_ctc_decode(const float* probs, int C, const int* toff, const int* tl
             if (dev >= 0 && dev < 64) configured[dev] = smem;
         }
     }
-    pdl_launch(ctc_decode_kernel, n, 128, smem, st, probs, C, toff, tlen, max_t, ids, id_len, score);
+    pdl_launch(ctc_decode_kernel, n, 128, smem, st, probs, C, cs, logits ? 1 : 0, toff, tlen, max_t, ids, id_len, score);
 }
 
 }  // namespace vse

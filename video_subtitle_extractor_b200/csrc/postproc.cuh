@@ -67,7 +67,8 @@ struct CropJob {
 void launch_crops(const CropJob* jobs_dev, int n_jobs, int max_pix, const short* cubic_tab, uint8_t* dst, cudaStream_t st);
 
 // probs: float32 [sum T][C]; toff/tlen per crop; ids [n][max_t]
-void launch_ctc_decode(const float* probs, int C, const int* toff, const int* tlen, int n, int max_t, int* ids, int* id_len,
-                       float* score, cudaStream_t st);
+// probs: [time steps][cs] rows of C class probabilities — or, logits = true, of class LOGITS (the softmax is folded into the decode)
+void launch_ctc_decode(const float* probs, int C, int cs, bool logits, const int* toff, const int* tlen, int n, int max_t, int* ids,
+                       int* id_len, float* score, cudaStream_t st);
 
 }  // namespace vse
