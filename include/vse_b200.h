@@ -105,6 +105,7 @@ typedef struct {
     float    timings_ms[8];  /* 0 h2d, 1 det-pre, 2 det-net, 3 det-post, 4 crop, 5 rec-net, 6 ctc+d2h, 7 total */
 } vse_result;
 
+/* Defaults: the reference's knobs as listed above, precision = VSE_PRECISION_FP32_TC (the parity mode), flags = 0. */
 void vse_default_config(vse_config* cfg);
 int  vse_abi_version(void);
 int  vse_device_count(void);

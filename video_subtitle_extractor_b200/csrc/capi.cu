@@ -46,7 +46,7 @@ void vse_default_config(vse_config* cfg) {
     if (!cfg) return;
     std::memset(cfg, 0, sizeof(*cfg));
     cfg->device = 0;
-    cfg->precision = VSE_PRECISION_FP16;
+    cfg->precision = VSE_PRECISION_FP32_TC;   // the mode that reproduces the reference's boxes and texts
     cfg->det_limit_side_len = 960;
     cfg->det_thresh = 0.3f;
     cfg->det_box_thresh = 0.6f;

@@ -132,7 +132,7 @@ def _i32(a) -> np.ndarray:
 class Engine:
     """One engine per (process, GPU) — mirrors the lifetime of PaddleOCR(...) in reference ocr.py:88-113."""
 
-    def __init__(self, device: int = 0, precision: int = PRECISION_FP16, rec_image_h: int = 48, rec_image_w: int = 320,
+    def __init__(self, device: int = 0, precision: int = PRECISION_FP32_TC, rec_image_h: int = 48, rec_image_w: int = 320,
                  rec_batch_num: int = 6, det_limit_side_len: int = 960, det_thresh: float = 0.3,
                  det_box_thresh: float = 0.6, det_unclip_ratio: float = 1.5, max_boxes_per_frame: int = 64,
                  max_text_len: int = 256, flags: int = 0):
