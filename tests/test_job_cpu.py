@@ -46,8 +46,8 @@ def _need(name):
     return os.path.join(VIDEOS, name)
 
 
-@pytest.mark.parametrize("world", [1, 3])
-def test_fast_mode_job_on_recorded_results(world):
+@pytest.mark.parametrize("world,decoders", [(1, 1), (3, 1), (1, 3), (2, 2)])
+def test_fast_mode_job_on_recorded_results(world, decoders):
     path = _need("test_en.mp4")
     with open(os.path.join(GOLDEN, "video_golden_test_en.json")) as f:
         vg = json.load(f)
@@ -57,8 +57,10 @@ def test_fast_mode_job_on_recorded_results(world):
     lines, numbers = [], []
     for rank in range(world):       # ranks run one after the other here; gather_by_frame is the identity without a process group
         eng = FakeEngine(vg["frames"])
+        # decoders > 1: the rank's schedule is cut into segments with one seeking decoder thread each; the fake engine finds
+        # every frame by its pixel sum, so a decoder that landed on the wrong frame after its seek fails the lookup
         res = job.fast_mode_job(eng, path, chars, rank=rank, world=world, batch=32, sub_area=tuple(g["area"]), pinned=False,
-                                write_srt=False)
+                                write_srt=False, decoders=decoders)
         lines += res.lines
         numbers += res.frame_numbers
         assert eng.prefetched == max(len(eng.calls) - 1, 0) and max(eng.calls) <= 32
@@ -68,14 +70,15 @@ def test_fast_mode_job_on_recorded_results(world):
     assert text == g["srt"]                                         # ... and its own generate_subtitle_file
 
 
-def test_accurate_mode_job_on_recorded_results():
+@pytest.mark.parametrize("decoders", [1, 2])
+def test_accurate_mode_job_on_recorded_results(decoders):
     path = _need("test_cn.mp4")
     with open(os.path.join(GOLDEN, "accurate_video_golden_test_cn.json"), encoding="utf-8") as f:
         g = json.load(f)
     eng = FakeEngine(g["frames"])
     res = job.accurate_mode_job(eng, path, charset.characters("ch", None, 6625), batch=64, sub_area=tuple(g["area"]),
-                                rec_char_type="ch", first=g["first"], last=g["last"], pinned=False)
-    assert eng.calls == [64, 32]
+                                rec_char_type="ch", first=g["first"], last=g["last"], pinned=False, decoders=decoders)
+    assert sorted(eng.calls, reverse=True) == [64, 32]
     assert [(t[0], t[1] is not None) for t in res.tasks] == [(t["frame_no"], t["cached"]) for t in g["tasks"]]
     assert res.lines == g["raw_lines"]
     assert res.srt == g["srt"]

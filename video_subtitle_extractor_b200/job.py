@@ -29,6 +29,13 @@ from . import accurate, dedup, frames as F, rawtxt, shard
 from .rawtxt import Coordinate
 
 
+def default_decoders(world: int = 1) -> int:
+    """Decoder threads per rank: up to four, leaving ~four host cores per decoder (every cv2 / ffmpeg capture spawns its own
+    frame threads) — fewer when several ranks share the host."""
+    import os
+    return max(1, min(4, (os.cpu_count() or 1) // (4 * max(world, 1))))
+
+
 def default_sub_area(h: int, w: int) -> Coordinate:
     """(xmin, xmax, ymin, ymax) of the reference's default subtitle area: fractions 0.78 / 0.99 / 0.05 / 0.95 (config.py:49)."""
     return int(w * 0.05), int(w * 0.95), int(h * 0.78), int(h * 0.99)
@@ -58,13 +65,17 @@ def _pinned_slot(index: int, shape) -> np.ndarray:
 
 
 class FrameFeed:
-    """Sequential batched decode of frames [first, last] (1-based, inclusive) of one video into pinned ring buffers.
+    """Batched decode of frames [first, last] (1-based, inclusive) of one video into pinned ring buffers.
 
-    `wanted`: the frame numbers to deliver (None = every frame of the range).  The decoder thread seeks once to the range
-    start (cv2 CAP_PROP_POS_FRAMES, what the reference's producer does per task) and then only reads forward."""
+    `wanted`: the frame numbers to deliver (None = every frame of the range).  A decoder thread seeks once to the start of its
+    range (cv2 CAP_PROP_POS_FRAMES, what the reference's producer does per task) and then only reads forward (`grab()` for the
+    frames nobody asked for).  `decoders` > 1 cuts the delivered frames into that many contiguous segments (whole batches) with
+    one decoder thread each: one cv2 / ffmpeg capture keeps only a few host cores busy, and with the engine in place decode is
+    the limiter of a whole-video job.  Batches then arrive in completion order, not frame order — every consumer here keys
+    results by frame number (run_feed)."""
 
     def __init__(self, path: str, first: int, last: int, wanted: Optional[Sequence[int]] = None, batch: int = 32, slots: int = 3,
-                 pinned: bool = True, half: Optional[str] = None, open_capture: Optional[Callable] = None):
+                 pinned: bool = True, half: Optional[str] = None, open_capture: Optional[Callable] = None, decoders: int = 1):
         import cv2
         self._open = open_capture or (lambda p: cv2.VideoCapture(p))
         cap = self._open(path)
@@ -77,6 +88,20 @@ class FrameFeed:
         self.path, self.first, self.last, self.batch = path, first, last, batch
         self.wanted = None if wanted is None else sorted(k for k in wanted if first <= k <= last)
         self.rows = F.half_frame_rows(half, self.h)
+        # segments: (first frame to decode, last frame to decode, frames to deliver or None = all), whole batches each
+        n_deliver = len(self.wanted) if self.wanted is not None else max(0, last - first + 1)
+        n_batches = -(-n_deliver // batch) if n_deliver else 0
+        k = max(1, min(int(decoders), n_batches)) if n_batches else 1
+        self._segments = []
+        for j in range(k):
+            lo, hi = (j * n_batches // k) * batch, min(((j + 1) * n_batches // k) * batch, n_deliver)
+            if self.wanted is not None:
+                seg = self.wanted[lo:hi]
+                # the first segment starts where the caller said (recorded timestamps cover the skipped lead-in, as before)
+                self._segments.append((first if j == 0 else seg[0], seg[-1], seg) if seg else (first, first - 1, []))
+            else:
+                self._segments.append((first + lo, first + hi - 1, None))
+        slots = max(slots, len(self._segments) + 2)
         self.slots = []
         for _ in range(slots):
             if pinned:
@@ -87,28 +112,35 @@ class FrameFeed:
         for s in range(slots):
             self._free.put(s)
         self._ready: "queue.Queue[Optional[Batch]]" = queue.Queue()
-        self.frames_read = 0
+        self._read = [0] * len(self._segments)
         self.msec: Dict[int, float] = {}          # decoder timestamp after reading frame `no` (what the SRT writer asks for)
         self._err: Optional[BaseException] = None
-        self._thread = threading.Thread(target=self._decode, daemon=True)
-        self._thread.start()
+        self._threads = [threading.Thread(target=self._decode, args=(j,), daemon=True) for j in range(len(self._segments))]
+        for t in self._threads:
+            t.start()
 
-    def _decode(self):
+    @property
+    def frames_read(self) -> int:
+        return sum(self._read)
+
+    def _decode(self, j: int):
         import cv2
+        seg_first, seg_last, seg_wanted = self._segments[j]
         try:
             cap = self._open(self.path)
-            if self.first > 1:
-                cap.set(cv2.CAP_PROP_POS_FRAMES, self.first - 1)
-            want = None if self.wanted is None else set(self.wanted)
-            stop = self.last if want is None else (max(want) if want else 0)
-            no = self.first - 1
+            if seg_first > 1:
+                cap.set(cv2.CAP_PROP_POS_FRAMES, seg_first - 1)
+            want = None if seg_wanted is None else set(seg_wanted)
+            stop = seg_last if want is None else (max(want) if want else 0)
+            no = seg_first - 1
             cur: Optional[Batch] = None
+            msec = {}
             while no < stop:
                 if not cap.grab():                 # frames that are not OCR tasks are decoded but never converted / copied
                     break
                 no += 1
-                self.frames_read += 1
-                self.msec[no] = cap.get(cv2.CAP_PROP_POS_MSEC)
+                self._read[j] += 1
+                msec[no] = cap.get(cv2.CAP_PROP_POS_MSEC)
                 if want is not None and no not in want:
                     continue
                 ok, frame = cap.retrieve()
@@ -125,6 +157,7 @@ class FrameFeed:
             if cur is not None and cur.numbers:
                 self._ready.put(cur)
             cap.release()
+            self.msec.update(msec)
         except BaseException as e:          # surfaced in the consumer
             self._err = e
         self._ready.put(None)
@@ -142,12 +175,14 @@ class FrameFeed:
         self._free.put(b.slot)
 
     def __iter__(self) -> Iterator[Batch]:
-        while True:
+        done = 0
+        while done < len(self._threads):
             b = self._ready.get()
             if b is None:
+                done += 1
                 if self._err is not None:
                     raise self._err
-                return
+                continue
             yield b
 
 
@@ -231,7 +266,7 @@ class JobResult:
 def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, world: int = 1, batch: int = 32,
                   sub_area: Optional[Coordinate] = "default", rec_char_type: str = "en", drop_score: float = 0.75,
                   extract_frequency: int = 3, threshold: float = 0.8, half: Optional[str] = None, pinned: bool = True,
-                  write_srt: bool = True, stats: Optional[dict] = None) -> JobResult:
+                  write_srt: bool = True, stats: Optional[dict] = None, decoders: Optional[int] = None) -> JobResult:
     """Fast mode of the reference (`run` -> `extract_frame_by_fps`, backend/main.py:145-147) on this rank's share of the
     schedule.  `sub_area` 'default' = the reference's default area for the video's size; None = no area."""
     import time
@@ -252,7 +287,8 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
     results: Dict[int, object] = {}
     feed = None
     if mine:
-        feed = FrameFeed(path, mine[0], mine[-1], mine, batch=batch, pinned=pinned, half=half)
+        feed = FrameFeed(path, mine[0], mine[-1], mine, batch=batch, pinned=pinned, half=half,
+                         decoders=default_decoders(world) if decoders is None else decoders)
         lap("feed_setup_s")
         results = run_feed(engine, feed, stats=stats)
     lap("run_feed_s")
@@ -274,7 +310,7 @@ def fast_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, w
 def accurate_mode_job(engine, path: str, characters: Sequence[str], rank: int = 0, world: int = 1, batch: int = 64,
                       sub_area: Optional[Coordinate] = "default", rec_char_type: str = "ch", drop_score: float = 0.75,
                       threshold: float = 0.8, first: int = 1, last: Optional[int] = None, pinned: bool = True,
-                      write_srt: bool = True, stats: Optional[dict] = None) -> JobResult:
+                      write_srt: bool = True, stats: Optional[dict] = None, decoders: Optional[int] = None) -> JobResult:
     """Accurate mode of the reference (`extract_frame_by_det`, backend/main.py:255-376): the detector looks at EVERY frame and
     the recogniser reads the frames the controller asks for.  Here det + rec run over every frame of this rank's range in
     batches (`vse_run`), the records are gathered by frame number and the reference's decisions are replayed
@@ -290,7 +326,8 @@ def accurate_mode_job(engine, path: str, characters: Sequence[str], rank: int = 
     results: Dict[int, object] = {}
     feed = None
     if hi > lo:
-        feed = FrameFeed(path, first + lo, first + hi - 1, None, batch=batch, pinned=pinned)
+        feed = FrameFeed(path, first + lo, first + hi - 1, None, batch=batch, pinned=pinned,
+                         decoders=default_decoders(world) if decoders is None else decoders)
         results = run_feed(engine, feed, stats=stats)
     local = [(no, ([q.tolist() for q in r.quads], [(ids_to_text(i, characters), float(s)) for i, s in zip(r.ids, r.rec_scores)]))
              for no, r in sorted(results.items())]
