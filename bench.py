@@ -617,7 +617,7 @@ def run_videos(args, rank, local_rank, world):
                       "video decoder through pinned host buffers, results go back to host text"},
               "per_rank": [{"rank": r, "frames_ocr": n, "s_per_step": round(w, 3), "feed_wait_s": round(fw, 3), "engine_s": round(es, 3),
                             "frames_decoded": fd, "phases_s": ph} for r, n, w, fw, es, fd, ph in per_rank],
-              "limiter": "video decode (one cv2 decoder thread per rank)" if mine[3] > mine[4] else "engine",
+              "limiter": f"video decode (cv2 / ffmpeg, {job.default_decoders(world)} decoder thread(s) per rank)" if mine[3] > mine[4] else "engine",
               "gpu_launches": launches})
 
 
