@@ -31,8 +31,10 @@ from .rawtxt import Coordinate
 
 def default_decoders(world: int = 1) -> int:
     """Decoder threads per rank: up to four, leaving ~four host cores per decoder (every cv2 / ffmpeg capture spawns its own
-    frame threads) — fewer when several ranks share the host."""
+    frame threads) — fewer when several ranks share the host.  VSE_DECODERS overrides."""
     import os
+    if os.environ.get("VSE_DECODERS"):
+        return max(1, int(os.environ["VSE_DECODERS"]))
     return max(1, min(4, (os.cpu_count() or 1) // (4 * max(world, 1))))
 
 
