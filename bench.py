@@ -543,7 +543,7 @@ VIDEO_JOBS = [("test_en.mp4", "en", "V4/en_rec_fast", 97), ("test_cn.mp4", "ch",
 
 
 def run_videos(args, rank, local_rank, world):
-    """One step = the four videos through job.fast_mode_job (decoder thread -> pinned ring -> vse_prefetch / vse_run ->
+    """One step = the four videos through job.fast_mode_job (decoder threads -> pinned ring -> vse_prefetch / vse_run ->
     raw.txt lines -> gather by frame -> de-dup -> .srt text on every rank).  Recognisers follow the reference's fallback chain
     (backend/tools/paddle_model_config.py:73-82).  value = OCR'd frames of all videos / wall time of the slowest rank."""
     import warnings

@@ -1,17 +1,23 @@
 // gemm_tc.cu — tcgen05 / TMA / TMEM implicit-GEMM convolution for sm_100a.
 //
 // The dense contractions of the shipped graphs (reference backend/models/*/inference.pdmodel: `conv2d` 1x1 / KxK stride 1,
-// `matmul_v2` — SURVEY.md Appendix B/F) run here on the 5th-generation tensor cores:
-//   A  = pixel-major fp16 activations, loaded by TMA straight into 128B-swizzled shared memory
-//        (1x1: 2-D tiles [128 pixels x 64 channels]; KxK: 4-D boxes [1 img][8 rows][16 cols][64 ch] shifted per filter
-//        tap — out-of-bounds rows/columns are zero-filled by TMA, which IS the convolution padding);
-//   B  = fp16 K-major weights [cout][tap][cin] (packed once per plan, L2-resident);
-//   D  = fp32 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1;
-//   epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld -> bias -> act -> affine -> +residual -> act -> fp16 store
-//        into the (possibly concat-aliased) output slice.
-// Persistent CTAs (one per SM) walk the tile list; warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2-5 = epilogue.  These nets are HBM-bound (35-59 FLOP/B): the point of the tensor cores is to get the FMA work
-// out of the way so that the kernel streams activations at memory speed.
+// `conv2d_transpose` 2x2 stride 2 as four 1x1 launches, `matmul_v2` — SURVEY.md Appendix B/F) run here on the 5th-generation
+// tensor cores:
+//   A  = pixel-major activations loaded by TMA straight into 128B-swizzled shared memory.  1x1: 2-D tiles [128 pixels x one
+//        128-byte K row]; KxK: 4-D boxes shifted per filter tap (out-of-bounds rows / columns are zero-filled by TMA, which IS
+//        the convolution padding) — one HALO box per k-block serving every tap (kernels up to 5x5), ROW boxes serving a group
+//        of vertical taps (7x7, 9x9), per-tap boxes otherwise; maps of height 1 (text lines) use 128 x 1 tiles;
+//   B  = K-major weights [cout][tap][cin], packed once per plan; resident in shared memory when small, else streamed per stage;
+//   D  = fp32 accumulators in a TMEM ring, so the epilogue of tile i overlaps the MMAs of the following tiles;
+//   epilogue (8 warps, two per TMEM lane quarter): tcgen05.ld -> bias -> act -> affine -> (+gate) -> +residual -> act ->
+//        128B-swizzled staging tile -> TMA store into the (possibly concat-aliased, possibly strided) output slice.
+// Operand modes: fp16 activations (kind::f16), fp32 activations as tf32 (kind::tf32), and the SPLIT mode the engine runs by
+// default — fp32 activations rewritten in shared memory by four transform warps as fp16 hi | lo rows, three kind::f16 MMAs per
+// product (or the stacked form: two operand fetches, four MMAs) — see conv_tc_kernel / umma_kblock.
+// Persistent CTAs (one per SM) walk the tile list; warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 =
+// epilogue, warps 10-13 = operand transform (split mode; optionally the fused depthwise stage).  The fast nets are HBM-bound
+// (35-59 FLOP/B): the point of the tensor cores is to get the FMA work out of the way so that the kernel streams activations
+// at memory speed; the server models (309-649 FLOP/B) are bound by the tensor pipe and the L2 -> shared-memory operand traffic.
 #include "gemm_tc.h"
 #include "pdl.cuh"
 

@@ -5,7 +5,7 @@ csrc/; this module only moves frames in and result records out):
 
 * `FrameFeed` — (f)1: the reference decodes one frame per OCR task (`ocr_task_producer`, reference
   backend/tools/subtitle_ocr.py:164-208: seek + read) or walks the video with `cap.read()` (`extract_frame_by_fps` /
-  `extract_frame_by_det`, backend/main.py:228-251, 275-283).  Here ONE decoder thread reads the rank's frame range
+  `extract_frame_by_det`, backend/main.py:228-251, 275-283).  Here up to four decoder threads (FrameFeed: contiguous segments of whole batches, one seeking capture each) read the rank's frame range
   sequentially into a ring of pinned batches; the consumer issues `vse_prefetch` for batch k+1 before `vse_run` of batch k,
   so decode, host->device copy and kernels overlap.  The half-frame crop of `frame_preprocess` (subtitle_ocr.py:270-289) is a
   zero-copy view (frames.sub_area_view).
