@@ -82,3 +82,27 @@ def test_accurate_mode_job_on_recorded_results(decoders):
     assert [(t[0], t[1] is not None) for t in res.tasks] == [(t["frame_no"], t["cached"]) for t in g["tasks"]]
     assert res.lines == g["raw_lines"]
     assert res.srt == g["srt"]
+
+
+def test_frame_feed_segments_cover_the_request_exactly():
+    """More decoders than batches, a ragged last batch, an empty request and a whole-range (wanted=None) feed: every requested
+    frame is delivered exactly once, whatever the number of decoder threads."""
+    path = _need("test_en.mp4")
+    wanted = list(range(100, 400, 7))            # 43 frames: batches of 8 -> 6 batches, the last one short
+    for k in (1, 2, 4, 9):
+        feed = job.FrameFeed(path, 90, 420, wanted, batch=8, pinned=False, decoders=k)
+        got = []
+        for b in feed:
+            assert 1 <= len(b.numbers) <= 8 and b.numbers == sorted(b.numbers)
+            got += b.numbers
+            feed.release(b)
+        assert sorted(got) == wanted and len(feed._segments) == min(k, 6)
+        assert all(n in feed.msec for n in wanted)
+    feed = job.FrameFeed(path, 1, 0, [], batch=4, pinned=False, decoders=3)
+    assert list(feed) == []
+    feed = job.FrameFeed(path, 50, 75, None, batch=8, pinned=False, decoders=3)      # every frame of the range
+    got = []
+    for b in feed:
+        got += b.numbers
+        feed.release(b)
+    assert sorted(got) == list(range(50, 76))
