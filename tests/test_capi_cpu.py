@@ -35,6 +35,8 @@ def test_default_config_mirrors_reference_knobs():
     assert (cfg.det_limit_side_len, cfg.rec_image_h, cfg.rec_image_w, cfg.rec_batch_num) == (960, 48, 320, 6)
     assert abs(cfg.det_thresh - 0.3) < 1e-7 and abs(cfg.det_box_thresh - 0.6) < 1e-7 and abs(cfg.det_unclip_ratio - 1.5) < 1e-7
     assert cfg.det_max_candidates == 1000
+    # the default mode is the one held to the parity bar (tests/test_gpu_real_video.py), not the faster fp16 storage
+    assert cfg.precision == E.PRECISION_FP32_TC == E.bench_mode()["precision"] and cfg.flags == 0
 
 
 def test_no_device_means_no_engine():
